@@ -1,0 +1,232 @@
+/*
+ * hana_b200.h — C ABI of the B200-native rasterisation path behind
+ * Hana-SoftwareRenderer's draw API.
+ *
+ * Every entry point replaces one piece of the reference's hot path
+ * (all citations relative to /root/reference/Hana-SoftwareRenderer/):
+ *
+ *   hana_draw            <- void graphics_draw_triangle(DrawData*)     graphics.h:15, graphics.cpp:378-407
+ *   hana_draw_model      <- DrawModel::draw(Camera*,RenderBuffer*,bool) scene.h:53-99 (shadow pass, main pass, shadow clear)
+ *   hana_sweep_*         <- the main loop calling Scene::tick per frame main.cpp:87-156 (batched: N frames per submission)
+ *   hana_rb_*            <- class RenderBuffer                          renderbuffer.h:5-22, renderbuffer.cpp:3-76
+ *   hana_model_upload    <- Model::vert/normal/uv(iface,nth) gathers    model.cpp:70,99,108 as read by graphics.cpp:383-385
+ *   hana_texture_upload  <- TGAImage storage read by TGAImage::get      tgaimage.cpp:248-253
+ *   HanaUniforms         <- struct ShaderData + struct Material         IShader.h:7-32
+ *   HANA_SHADER_*        <- the IShader subclasses                      IShader.h:132-165, IShader.cpp
+ *
+ * Plain pointers and sizes only; no C++ or torch types. All functions return
+ * 0 on success, a negative HANA_E_* code otherwise; hana_last_error() gives
+ * the message of the last failure on the calling thread. There is no CPU
+ * fallback: without a CUDA device every compute entry point fails.
+ *
+ * Threading: one context per GPU; calls on one context must be serialised by
+ * the caller (the reference is single-threaded: SURVEY.md §8b).
+ */
+#ifndef HANA_B200_H
+#define HANA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HANA_OK 0
+#define HANA_E_INVALID (-1)   /* bad argument */
+#define HANA_E_CUDA (-2)      /* CUDA runtime/driver error (message has the cudaError string) */
+#define HANA_E_NODEVICE (-3)  /* no usable CUDA device: there is no CPU fallback */
+#define HANA_E_UNSUPPORTED (-4) /* e.g. an IShader subclass outside the closed device set */
+#define HANA_E_OVERFLOW (-5)  /* internal capacity exceeded even after the automatic retry */
+
+/* The closed set of device shaders (IShader.cpp). User-defined IShader
+ * subclasses cannot run on the device and are rejected by the shim. */
+#define HANA_SHADER_SHADOW 0        /* ShadowShader            IShader.cpp:170-180 */
+#define HANA_SHADER_BLINN 1         /* BlinnShader             IShader.cpp:85-109  */
+#define HANA_SHADER_NORMALMAP 2     /* NormalMapShader         IShader.cpp:117-162 */
+#define HANA_SHADER_GROUND 3        /* GroundShader            IShader.cpp:5-15    */
+#define HANA_SHADER_TOON 4          /* ToonShader              IShader.cpp:23-39   */
+#define HANA_SHADER_TEXTURE 5       /* TextureShader           IShader.cpp:47-57   */
+#define HANA_SHADER_TEXTURE_LIGHT 6 /* TextureWithLightShader  IShader.cpp:65-77   */
+#define HANA_SHADER_COUNT 7
+
+/* POD image of ShaderData (IShader.h:17-32) + Material scalars (IShader.h:7-15).
+ * Matrices are row-major float[16] exactly as Matrix4x4 rows[4] lie in memory
+ * (matrix.h:31). The library forms camera_vp*model and light_vp*model on the
+ * host with the reference's own evaluation order (matrix.h:118-123,
+ * vector.h:69-73), which gives the bits IShader.h:56,60 produce per vertex. */
+typedef struct HanaUniforms {
+    float model[16];        /* ShaderData::model_matrix     */
+    float model_I[16];      /* ShaderData::model_matrix_I   */
+    float camera_vp[16];    /* ShaderData::camera_vp_matrix */
+    float light_vp[16];     /* ShaderData::light_vp_matrix  */
+    float view_pos[3];      /* ShaderData::view_Pos         */
+    float gloss;            /* Material::gloss              */
+    float light_dir[3];     /* ShaderData::light_dir        */
+    float bump_scale;       /* Material::bump_scale         */
+    float light_color[4];   /* ShaderData::light_color (r,g,b,a) */
+    float ambient[4];       /* ShaderData::ambient          */
+    float mat_color[4];     /* Material::color              */
+    float mat_specular[4];  /* Material::specular           */
+    int32_t enable_shadow;  /* ShaderData::enable_shadow    */
+    int32_t reserved[3];
+} HanaUniforms;
+
+/* Per-draw counters (device-side, read back on request). */
+typedef struct HanaStats {
+    uint32_t faces_in;        /* faces submitted                              */
+    uint32_t tris_clipped;    /* faces that went through Sutherland-Hodgman   */
+    uint32_t tris_out;        /* triangles after clip+cull+degenerate reject  */
+    uint32_t tile_refs;       /* (tile, triangle) pairs binned                */
+    uint32_t tiles_touched;   /* 16x16 tiles with at least one triangle       */
+    uint32_t pixels_covered;  /* pixels whose final value was written by this draw */
+    uint32_t overflow;        /* non-zero if a capacity retry happened        */
+    uint32_t reserved;
+} HanaStats;
+
+typedef struct hana_ctx hana_ctx;
+typedef struct hana_model hana_model;
+typedef struct hana_texture hana_texture;
+typedef struct hana_rb hana_rb;
+typedef struct hana_sweep hana_sweep;
+
+const char* hana_last_error(void);
+int hana_version(void);
+int hana_device_count(void);
+
+/* --- context ------------------------------------------------------------ */
+int hana_ctx_create(int device, hana_ctx** out);
+int hana_ctx_destroy(hana_ctx* ctx);
+/* Launch on an existing cudaStream_t (e.g. torch's current stream) instead of
+ * the context's own non-blocking stream; pass NULL to go back. */
+int hana_ctx_set_stream(hana_ctx* ctx, void* cuda_stream);
+int hana_sync(hana_ctx* ctx);
+/* Number of kernels this context has launched so far (bench "gpu_launches"). */
+int hana_ctx_launch_count(hana_ctx* ctx, uint64_t* out);
+
+/* --- inputs --------------------------------------------------------------- */
+/* a2v: ncorners records of shader_struct_a2v (IShader.h:35-39): 8 floats
+ * {obj_pos.xyz, obj_normal.xyz, uv.xy}, 3 consecutive corners per face in the
+ * order graphics.cpp:380-386 visits them. ncorners must be a multiple of 3. */
+int hana_model_upload(hana_ctx* ctx, const float* a2v, int ncorners, hana_model** out);
+int hana_model_destroy(hana_model* m);
+int hana_model_ncorners(const hana_model* m);
+
+/* data: TGAImage::buffer() layout (tgaimage.cpp:248-253): w*h texels of
+ * bytespp (1, 3 or 4) bytes in B,G,R,A order, row y at data + y*w*bytespp. */
+int hana_texture_upload(hana_ctx* ctx, const uint8_t* data, int w, int h, int bytespp,
+                        hana_texture** out);
+int hana_texture_destroy(hana_texture* t);
+
+/* --- render target (RenderBuffer, renderbuffer.h:5-22) -------------------- */
+/* Device-resident colour (RGBA8, index (y*w+x)*4, y up) + depth (f32, y*w+x).
+ * A fresh buffer holds what the reference ctor leaves: colour (0,0,0,255),
+ * depth 1.0 (renderbuffer.cpp:6-7,16-17). */
+int hana_rb_create(hana_ctx* ctx, int width, int height, hana_rb** out);
+int hana_rb_destroy(hana_rb* rb);
+int hana_rb_size(const hana_rb* rb, int* width, int* height);
+/* renderbuffer_clear_color writes all four bytes (renderbuffer.cpp:59-68);
+ * the bytes are given directly because Color{...,a=255}*255 is out of range
+ * for unsigned char in the reference. */
+int hana_rb_clear_color(hana_rb* rb, uint8_t r, uint8_t g, uint8_t b, uint8_t a);
+int hana_rb_clear_depth(hana_rb* rb, float depth);
+/* Either pointer may be NULL to skip that plane. Host pointers; synchronous. */
+int hana_rb_upload(hana_rb* rb, const uint8_t* color_rgba, const float* depth);
+int hana_rb_download(hana_rb* rb, uint8_t* color_rgba, float* depth);
+/* Raw device pointers (for zero-copy consumers such as the bench harness). */
+int hana_rb_device_ptrs(hana_rb* rb, void** color_dev, void** depth_dev);
+
+/* --- the draw entry points -------------------------------------------------- */
+/* One pass over all faces of `model` with device shader `shader_id`:
+ * vertex -> clip -> cull -> setup -> bin -> tile raster + depth test +
+ * fragment shading -> tile flush. Semantics are those of
+ * graphics_draw_triangle (graphics.cpp:378-407): existing contents of `rb`
+ * take part in the depth test, only covered pixels change (R,G,B and depth;
+ * alpha is never written). diffuse/normal may be NULL (fetches return 0 as
+ * TGAImage::get does without data); shadow_map may be NULL
+ * (IShader.h:109 -> lit). Asynchronous on the context's stream. */
+int hana_draw(hana_ctx* ctx, hana_rb* rb, const hana_model* model, int shader_id,
+              const HanaUniforms* uniforms, const hana_texture* diffuse,
+              const hana_texture* normal, const hana_rb* shadow_map);
+
+/* DrawModel::draw (scene.h:53-99): if u->enable_shadow, ShadowShader pass
+ * into `shadow_map`, then `shader_id` pass into `frame` reading it, then
+ * shadow_map cleared to (0,0,0,[255*255 -> 1]) / FLT_MAX (scene.h:94-98). */
+int hana_draw_model(hana_ctx* ctx, hana_rb* frame, hana_rb* shadow_map, const hana_model* model,
+                    int shader_id, const HanaUniforms* uniforms, const hana_texture* diffuse,
+                    const hana_texture* normal);
+
+/* Same as hana_draw_model but with HOST render buffers, exactly the memory
+ * the reference's DrawModel::draw reads and writes: frame colour/depth are
+ * uploaded, both passes run, results are downloaded back (the shadow map's
+ * final state is the cleared one, so it is not transferred). This is the
+ * call the drop-in graphics_draw_triangle shim and the bench's e2e leg use.
+ * If assume_cleared != 0 the frame is taken to hold (clear_rgba, clear_depth)
+ * everywhere and the upload is skipped. */
+int hana_draw_model_host(hana_ctx* ctx, int width, int height, uint8_t* frame_color_rgba,
+                         float* frame_depth, const hana_model* model, int shader_id,
+                         const HanaUniforms* uniforms, const hana_texture* diffuse,
+                         const hana_texture* normal, int assume_cleared,
+                         const uint8_t clear_rgba[4], float clear_depth);
+
+int hana_last_stats(hana_ctx* ctx, HanaStats* out); /* synchronises */
+
+/* --- batched frame sweep (BASELINE.json configs[2]) ------ */
+/* Renders n_frames independent frames of one model per submission: for each
+ * frame clear (clear_rgba, clear_depth), optional shadow pass, main pass —
+ * i.e. main.cpp:152-153 + DrawModel::draw — with the frame index as a grid
+ * dimension, so launch latency is paid once per batch. Frames land in a
+ * device ring of `n_frames` colour+depth targets. */
+int hana_sweep_create(hana_ctx* ctx, int width, int height, int max_frames, hana_sweep** out);
+int hana_sweep_destroy(hana_sweep* s);
+/* uniforms: host array of n_frames HanaUniforms (copied H2D inside). */
+int hana_sweep_render(hana_sweep* s, const hana_model* model, int shader_id,
+                      const HanaUniforms* uniforms, int n_frames, const hana_texture* diffuse,
+                      const hana_texture* normal, const uint8_t clear_rgba[4], float clear_depth);
+/* Same, uniforms already resident on the device (n_frames * sizeof(HanaUniforms)). */
+int hana_sweep_render_dev(hana_sweep* s, const hana_model* model, int shader_id,
+                          const void* uniforms_dev, int n_frames, const hana_texture* diffuse,
+                          const hana_texture* normal, const uint8_t clear_rgba[4], float clear_depth);
+/* Copy frame `i` of the last batch to host (either may be NULL). Synchronous. */
+int hana_sweep_download(hana_sweep* s, int frame, uint8_t* color_rgba, float* depth);
+/* Async copy of frames [first, first+count) into caller-provided PINNED host
+ * memory (count*W*H*4 bytes each plane; depth may be NULL); ordered on the
+ * context's stream. */
+int hana_sweep_download_async(hana_sweep* s, int first, int count, uint8_t* color_rgba_pinned,
+                              float* depth_pinned);
+int hana_sweep_device_ptrs(hana_sweep* s, void** color_dev, void** depth_dev,
+                           size_t* frame_stride_pixels);
+/* Per-frame 64-bit checksum (FNV-style over RGB bytes and depth bits) of the
+ * last batch, computed on the device; used by the multi-GPU sharding tests. */
+int hana_sweep_checksums(hana_sweep* s, int n_frames, uint64_t* out_host);
+int hana_sweep_stats(hana_sweep* s, int frame, HanaStats* out); /* synchronises */
+
+/* Pinned host memory helpers for the e2e path. */
+int hana_host_alloc(size_t bytes, void** out);
+int hana_host_free(void* p);
+
+/* --- stage-level entry points (parity tests, SURVEY.md §4 tier 1) --------- */
+/* Runs only the vertex kernel; out_v2f receives ncorners records of
+ * shader_struct_v2f (IShader.h:41-47): 13 floats each. Fields the shader
+ * does not set are written as 0. */
+int hana_stage_vertex(hana_ctx* ctx, const hana_model* model, int shader_id,
+                      const HanaUniforms* uniforms, float* out_v2f_host);
+/* Runs vertex + clip + cull + setup for a `width` x `height` target and
+ * returns the surviving triangles sorted by order key: per triangle
+ * 1 order key (face*8 + fan index) in out_order, and 3x13 floats of the
+ * post-clip v2f records in out_v2f (capacity in triangles). */
+int hana_stage_setup(hana_ctx* ctx, const hana_model* model, int shader_id,
+                     const HanaUniforms* uniforms, int width, int height, int capacity,
+                     uint32_t* out_order, float* out_v2f, int* out_count);
+/* Primitive-ID buffer of the last hana_draw on `rb` is not kept by the
+ * reference; this variant of hana_draw also writes, per pixel, the order key
+ * of the primitive that owns it (0xFFFFFFFF where the draw wrote nothing). */
+int hana_draw_primid(hana_ctx* ctx, hana_rb* rb, const hana_model* model, int shader_id,
+                     const HanaUniforms* uniforms, const hana_texture* diffuse,
+                     const hana_texture* normal, const hana_rb* shadow_map,
+                     uint32_t* out_primid_host);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HANA_B200_H */
