@@ -1,0 +1,1248 @@
+/*
+ * hana_b200.cu — the C ABI of include/hana_b200.h over the kernels in
+ * hana_kernels.cuh. Host side only: device memory, tensor maps, pass
+ * sequencing, capacity management. No rendering arithmetic happens here and
+ * there is no CPU fallback: without a CUDA device every entry point fails
+ * with HANA_E_NODEVICE.
+ *
+ * Pass sequencing mirrors DrawModel::draw (scene.h:53-99): ShadowShader pass,
+ * then the shaded pass reading its colour plane, then the shadow-map clear.
+ */
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "hana_kernels.cuh"
+
+using namespace hana;
+
+#define HANA_VERSION_NUM 100
+
+/* ---- errors ------------------------------------------------------------------ */
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+#define CU_TRY(expr)                                                                                             \
+    do {                                                                                                         \
+        cudaError_t e__ = (expr);                                                                                \
+        if (e__ != cudaSuccess)                                                                                  \
+            return fail(e__ == cudaErrorNoDevice || e__ == cudaErrorInsufficientDriver ? HANA_E_NODEVICE : HANA_E_CUDA, \
+                        std::string(#expr) + ": " + cudaGetErrorString(e__));                                    \
+    } while (0)
+#define HANA_TRY(expr)            \
+    do {                          \
+        int r__ = (expr);         \
+        if (r__ != HANA_OK) return r__; \
+    } while (0)
+
+/* ---- objects ------------------------------------------------------------------ */
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+enum ProfKind { PROF_BEGIN = 0, PROF_SETUP, PROF_SCAN, PROF_FILL, PROF_RASTER_SHADOW, PROF_RASTER_MAIN, PROF_OTHER, PROF_KINDS };
+
+struct Scratch {
+    TriRecord* tri_rec = nullptr;
+    float4* tri_attr = nullptr;
+    size_t tri_total = 0; /* records allocated (n_frames * tri_cap) */
+    size_t attr_total = 0;
+    uint32_t* tri_count = nullptr;
+    size_t frames_cap = 0;
+    uint32_t* tile_arrays = nullptr; /* count | cursor | offset, each n_frames * n_tiles */
+    size_t tile_arr_cap = 0;
+    uint32_t* refs = nullptr;
+    size_t pool_cap = 0;
+    uint32_t* work = nullptr;
+    size_t work_cap = 0;
+    PassCounters* counters = nullptr;
+    PassCounters* counters_host = nullptr; /* pinned */
+};
+
+struct hana_ctx {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    uint64_t launches = 0;
+    bool use_tma = true;
+    EncodeTiledFn encode = nullptr;
+    Scratch sc;
+    uint32_t tri_cap_hint = 0;
+    HanaUniforms* u_raw = nullptr;  /* device, 1 */
+    DevUniforms* u_dev = nullptr;   /* device, 1 */
+    uint32_t* stat_pixels = nullptr; /* device, 1 */
+    HanaStats last_stats;
+    bool profile = false;
+    struct ProfEv {
+        cudaEvent_t a, b;
+        int kind;
+    };
+    std::vector<ProfEv> prof_pending;
+    std::vector<cudaEvent_t> ev_pool;
+    double prof_ms[PROF_KINDS] = {0};
+    uint64_t prof_n[PROF_KINDS] = {0};
+    cudaEvent_t t0 = nullptr, t1 = nullptr;
+    /* host-buffer path cache */
+    hana_sweep* host_sweep = nullptr;
+    hana_rb* host_frame = nullptr;
+    hana_rb* host_shadow = nullptr;
+    int occ[HANA_SHADER_COUNT][3];
+};
+
+struct hana_model {
+    hana_ctx* ctx;
+    float4* posu;
+    float4* nrmv;
+    int ncorners;
+};
+struct hana_texture {
+    hana_ctx* ctx;
+    uint32_t* texels;
+    int w, h;
+};
+struct hana_rb {
+    hana_ctx* ctx;
+    int w, h;
+    uint32_t* color;
+    float* depth;
+    bool tma_ok;
+    CUtensorMap tm_color, tm_depth;
+};
+struct hana_sweep {
+    hana_ctx* ctx;
+    int w, h, max_frames;
+    uint32_t* color;
+    float* depth;
+    uint8_t* shadow_r8;
+    int shadow_pitch;
+    size_t shadow_frame_bytes;
+    bool tma_ok;
+    CUtensorMap tm_color, tm_depth, tm_r8;
+    HanaUniforms* u_raw;
+    DevUniforms* u_dev;
+    unsigned long long* checksums;
+    uint32_t* pix_counts;
+    int last_frames;
+    float last_clear_depth;
+    HanaStats last_stats; /* frame-independent part */
+    std::vector<uint32_t> last_tri_counts[2];
+};
+
+extern "C" const char* hana_last_error(void) { return g_err.c_str(); }
+extern "C" int hana_version(void) { return HANA_VERSION_NUM; }
+extern "C" int hana_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+/* ---- tensor maps ---------------------------------------------------------------- */
+static int make_tensor_map(hana_ctx* ctx, CUtensorMap* tm, CUtensorMapDataType dt, int elem_bytes, void* base, uint64_t w,
+                           uint64_t h, uint64_t frames, uint64_t row_bytes, uint64_t frame_bytes) {
+    memset(tm, 0, sizeof(*tm));
+    if (!ctx->encode) return fail(HANA_E_CUDA, "cuTensorMapEncodeTiled unavailable");
+    cuuint64_t dims[3] = {w, h, frames};
+    cuuint64_t strides[2] = {row_bytes, frame_bytes};
+    cuuint32_t box[3] = {TILE, TILE, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    (void)elem_bytes;
+    CUresult r = ctx->encode(tm, dt, 3, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(HANA_E_CUDA, "cuTensorMapEncodeTiled failed: " + std::to_string((int)r));
+    return HANA_OK;
+}
+
+/* ---- context ------------------------------------------------------------------- */
+static int use_device(hana_ctx* ctx) {
+    CU_TRY(cudaSetDevice(ctx->device));
+    return HANA_OK;
+}
+
+extern "C" int hana_ctx_create(int device, hana_ctx** out) {
+    if (!out) return fail(HANA_E_INVALID, "out is NULL");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        return fail(HANA_E_NODEVICE, std::string("no CUDA device (there is no CPU fallback): ") +
+                                         (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0"));
+    }
+    if (device < 0 || device >= n) return fail(HANA_E_INVALID, "device ordinal out of range");
+    hana_ctx* ctx = new (std::nothrow) hana_ctx();
+    if (!ctx) return fail(HANA_E_INVALID, "out of host memory");
+    ctx->device = device;
+    memset(&ctx->last_stats, 0, sizeof(ctx->last_stats));
+    for (auto& a : ctx->occ)
+        for (int& b : a) b = 0;
+    CU_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) {
+        delete ctx;
+        return fail(HANA_E_NODEVICE, std::string("device is sm_") + std::to_string(prop.major * 10 + prop.minor) +
+                                         "; this library contains sm_100a code only");
+    }
+    ctx->sm_count = prop.multiProcessorCount;
+    CU_TRY(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
+    ctx->stream = ctx->own_stream;
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr) == cudaSuccess &&
+        qr == cudaDriverEntryPointSuccess)
+        ctx->encode = (EncodeTiledFn)fn;
+    else
+        cudaGetLastError();
+    const char* no_tma = getenv("HANA_NO_TMA");
+    ctx->use_tma = ctx->encode != nullptr && !(no_tma && no_tma[0] == '1');
+    CU_TRY(cudaMalloc(&ctx->u_raw, sizeof(HanaUniforms)));
+    CU_TRY(cudaMalloc(&ctx->u_dev, sizeof(DevUniforms)));
+    CU_TRY(cudaMalloc(&ctx->stat_pixels, sizeof(uint32_t)));
+    CU_TRY(cudaMalloc(&ctx->sc.counters, sizeof(PassCounters)));
+    CU_TRY(cudaMallocHost(&ctx->sc.counters_host, sizeof(PassCounters)));
+    CU_TRY(cudaEventCreate(&ctx->t0));
+    CU_TRY(cudaEventCreate(&ctx->t1));
+    *out = ctx;
+    return HANA_OK;
+}
+
+extern "C" int hana_sweep_destroy(hana_sweep* s);
+extern "C" int hana_rb_destroy(hana_rb* rb);
+
+extern "C" int hana_ctx_destroy(hana_ctx* ctx) {
+    if (!ctx) return HANA_OK;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    if (ctx->host_sweep) hana_sweep_destroy(ctx->host_sweep);
+    if (ctx->host_frame) hana_rb_destroy(ctx->host_frame);
+    if (ctx->host_shadow) hana_rb_destroy(ctx->host_shadow);
+    Scratch& s = ctx->sc;
+    cudaFree(s.tri_rec); cudaFree(s.tri_attr); cudaFree(s.tri_count); cudaFree(s.tile_arrays);
+    cudaFree(s.refs); cudaFree(s.work); cudaFree(s.counters); cudaFreeHost(s.counters_host);
+    cudaFree(ctx->u_raw); cudaFree(ctx->u_dev); cudaFree(ctx->stat_pixels);
+    for (auto& p : ctx->prof_pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
+    for (auto e : ctx->ev_pool) cudaEventDestroy(e);
+    cudaEventDestroy(ctx->t0); cudaEventDestroy(ctx->t1);
+    cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+    return HANA_OK;
+}
+
+extern "C" int hana_ctx_set_stream(hana_ctx* ctx, void* cuda_stream) {
+    if (!ctx) return fail(HANA_E_INVALID, "ctx is NULL");
+    HANA_TRY(use_device(ctx));
+    CU_TRY(cudaStreamSynchronize(ctx->stream));
+    ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    return HANA_OK;
+}
+extern "C" int hana_sync(hana_ctx* ctx) {
+    if (!ctx) return fail(HANA_E_INVALID, "ctx is NULL");
+    HANA_TRY(use_device(ctx));
+    CU_TRY(cudaStreamSynchronize(ctx->stream));
+    return HANA_OK;
+}
+extern "C" int hana_ctx_launch_count(hana_ctx* ctx, uint64_t* out) {
+    if (!ctx || !out) return fail(HANA_E_INVALID, "NULL argument");
+    *out = ctx->launches;
+    return HANA_OK;
+}
+extern "C" int hana_ctx_uses_tma(hana_ctx* ctx) { return ctx && ctx->use_tma ? 1 : 0; }
+extern "C" int hana_ctx_set_tma(hana_ctx* ctx, int enable) {
+    if (!ctx) return fail(HANA_E_INVALID, "ctx is NULL");
+    ctx->use_tma = enable && ctx->encode;
+    return HANA_OK;
+}
+extern "C" int hana_ctx_sm_count(hana_ctx* ctx) { return ctx ? ctx->sm_count : 0; }
+
+/* ---- profiling (CUDA events around each kernel class, on the launching stream) ---- */
+static void prof_begin(hana_ctx* ctx, int kind, cudaEvent_t* a, cudaEvent_t* b) {
+    *a = *b = nullptr;
+    if (!ctx->profile) return;
+    auto get = [&]() {
+        cudaEvent_t e = nullptr;
+        if (!ctx->ev_pool.empty()) {
+            e = ctx->ev_pool.back();
+            ctx->ev_pool.pop_back();
+        } else {
+            cudaEventCreate(&e);
+        }
+        return e;
+    };
+    *a = get();
+    *b = get();
+    cudaEventRecord(*a, ctx->stream);
+    (void)kind;
+}
+static void prof_end(hana_ctx* ctx, int kind, cudaEvent_t a, cudaEvent_t b) {
+    if (!a) return;
+    cudaEventRecord(b, ctx->stream);
+    ctx->prof_pending.push_back({a, b, kind});
+}
+static void prof_resolve(hana_ctx* ctx) {
+    for (auto& p : ctx->prof_pending) {
+        float ms = 0.f;
+        if (cudaEventSynchronize(p.b) == cudaSuccess && cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) {
+            ctx->prof_ms[p.kind] += ms;
+            ctx->prof_n[p.kind] += 1;
+        }
+        ctx->ev_pool.push_back(p.a);
+        ctx->ev_pool.push_back(p.b);
+    }
+    ctx->prof_pending.clear();
+}
+extern "C" int hana_ctx_profile(hana_ctx* ctx, int enable) {
+    if (!ctx) return fail(HANA_E_INVALID, "ctx is NULL");
+    HANA_TRY(use_device(ctx));
+    prof_resolve(ctx);
+    ctx->profile = enable != 0;
+    return HANA_OK;
+}
+extern "C" int hana_ctx_profile_reset(hana_ctx* ctx) {
+    if (!ctx) return fail(HANA_E_INVALID, "ctx is NULL");
+    HANA_TRY(use_device(ctx));
+    prof_resolve(ctx);
+    for (int i = 0; i < PROF_KINDS; i++) {
+        ctx->prof_ms[i] = 0;
+        ctx->prof_n[i] = 0;
+    }
+    return HANA_OK;
+}
+extern "C" int hana_ctx_profile_get(hana_ctx* ctx, int kind, double* total_ms, uint64_t* launches) {
+    if (!ctx || kind < 0 || kind >= PROF_KINDS) return fail(HANA_E_INVALID, "bad argument");
+    HANA_TRY(use_device(ctx));
+    prof_resolve(ctx);
+    if (total_ms) *total_ms = ctx->prof_ms[kind];
+    if (launches) *launches = ctx->prof_n[kind];
+    return HANA_OK;
+}
+extern "C" int hana_timer_start(hana_ctx* ctx) {
+    if (!ctx) return fail(HANA_E_INVALID, "ctx is NULL");
+    HANA_TRY(use_device(ctx));
+    CU_TRY(cudaEventRecord(ctx->t0, ctx->stream));
+    return HANA_OK;
+}
+extern "C" int hana_timer_stop(hana_ctx* ctx, float* ms) {
+    if (!ctx || !ms) return fail(HANA_E_INVALID, "NULL argument");
+    HANA_TRY(use_device(ctx));
+    CU_TRY(cudaEventRecord(ctx->t1, ctx->stream));
+    CU_TRY(cudaEventSynchronize(ctx->t1));
+    CU_TRY(cudaEventElapsedTime(ms, ctx->t0, ctx->t1));
+    return HANA_OK;
+}
+
+/* ---- inputs ----------------------------------------------------------------------- */
+extern "C" int hana_model_upload(hana_ctx* ctx, const float* a2v, int ncorners, hana_model** out) {
+    if (!ctx || !out || (!a2v && ncorners > 0)) return fail(HANA_E_INVALID, "NULL argument");
+    if (ncorners < 0 || ncorners % 3 != 0) return fail(HANA_E_INVALID, "ncorners must be a non-negative multiple of 3");
+    if (ncorners / 3 >= (1 << 28)) return fail(HANA_E_INVALID, "too many faces for the 32-bit order key");
+    HANA_TRY(use_device(ctx));
+    hana_model* m = new hana_model{ctx, nullptr, nullptr, ncorners};
+    size_t n = (size_t)std::max(ncorners, 1);
+    /* AoS a2v records -> two SoA float4 streams */
+    std::vector<float4> posu(n), nrmv(n);
+    for (int i = 0; i < ncorners; i++) {
+        const float* a = a2v + (size_t)i * 8;
+        posu[i] = make_float4(a[0], a[1], a[2], a[6]);
+        nrmv[i] = make_float4(a[3], a[4], a[5], a[7]);
+    }
+    cudaError_t e1 = cudaMalloc(&m->posu, n * sizeof(float4));
+    cudaError_t e2 = cudaMalloc(&m->nrmv, n * sizeof(float4));
+    if (e1 != cudaSuccess || e2 != cudaSuccess) {
+        cudaFree(m->posu); cudaFree(m->nrmv);
+        delete m;
+        cudaGetLastError();
+        return fail(HANA_E_CUDA, "cudaMalloc failed for the model streams");
+    }
+    CU_TRY(cudaMemcpyAsync(m->posu, posu.data(), n * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
+    CU_TRY(cudaMemcpyAsync(m->nrmv, nrmv.data(), n * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
+    CU_TRY(cudaStreamSynchronize(ctx->stream));
+    *out = m;
+    return HANA_OK;
+}
+extern "C" int hana_model_destroy(hana_model* m) {
+    if (!m) return HANA_OK;
+    cudaSetDevice(m->ctx->device);
+    cudaFree(m->posu);
+    cudaFree(m->nrmv);
+    delete m;
+    return HANA_OK;
+}
+extern "C" int hana_model_ncorners(const hana_model* m) { return m ? m->ncorners : 0; }
+
+extern "C" int hana_texture_upload(hana_ctx* ctx, const uint8_t* data, int w, int h, int bytespp, hana_texture** out) {
+    if (!ctx || !out || !data) return fail(HANA_E_INVALID, "NULL argument");
+    if (w <= 0 || h <= 0 || (bytespp != 1 && bytespp != 3 && bytespp != 4))
+        return fail(HANA_E_INVALID, "texture must be w,h > 0 with 1, 3 or 4 bytes per texel");
+    HANA_TRY(use_device(ctx));
+    size_t n = (size_t)w * h;
+    std::vector<uint32_t> tex(n);
+    for (size_t i = 0; i < n; i++) { /* TGAColor(p, bpp): bytes beyond bpp stay 0 (tgaimage.h:46-53) */
+        uint32_t v = 0;
+        for (int b = 0; b < bytespp; b++) v |= (uint32_t)data[i * bytespp + b] << (8 * b);
+        tex[i] = v;
+    }
+    hana_texture* t = new hana_texture{ctx, nullptr, w, h};
+    if (cudaMalloc(&t->texels, n * 4) != cudaSuccess) {
+        delete t;
+        cudaGetLastError();
+        return fail(HANA_E_CUDA, "cudaMalloc failed for the texture");
+    }
+    CU_TRY(cudaMemcpyAsync(t->texels, tex.data(), n * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CU_TRY(cudaStreamSynchronize(ctx->stream));
+    *out = t;
+    return HANA_OK;
+}
+extern "C" int hana_texture_destroy(hana_texture* t) {
+    if (!t) return HANA_OK;
+    cudaSetDevice(t->ctx->device);
+    cudaFree(t->texels);
+    delete t;
+    return HANA_OK;
+}
+
+/* ---- launches ------------------------------------------------------------------ */
+static int launch_fill32(hana_ctx* ctx, uint32_t* dst, uint32_t value, size_t n) {
+    if (n == 0) return HANA_OK;
+    int blocks = (int)std::min<size_t>((n / 4 + 255) / 256 + 1, (size_t)ctx->sm_count * 16);
+    cudaEvent_t a, b;
+    prof_begin(ctx, PROF_OTHER, &a, &b);
+    fill32_kernel<<<blocks, 256, 0, ctx->stream>>>(dst, value, n);
+    prof_end(ctx, PROF_OTHER, a, b);
+    ctx->launches++;
+    CU_TRY(cudaGetLastError());
+    return HANA_OK;
+}
+
+/* ---- render targets ---------------------------------------------------------------- */
+extern "C" int hana_rb_create(hana_ctx* ctx, int width, int height, hana_rb** out) {
+    if (!ctx || !out) return fail(HANA_E_INVALID, "NULL argument");
+    if (width <= 0 || height <= 0 || width > 65535 || height > 65535)
+        return fail(HANA_E_INVALID, "render buffer size must be in 1..65535");
+    HANA_TRY(use_device(ctx));
+    hana_rb* rb = new hana_rb();
+    rb->ctx = ctx;
+    rb->w = width;
+    rb->h = height;
+    rb->color = nullptr;
+    rb->depth = nullptr;
+    size_t n = (size_t)width * height;
+    if (cudaMalloc(&rb->color, n * 4) != cudaSuccess || cudaMalloc(&rb->depth, n * 4) != cudaSuccess) {
+        cudaFree(rb->color);
+        delete rb;
+        cudaGetLastError();
+        return fail(HANA_E_CUDA, "cudaMalloc failed for the render buffer");
+    }
+    rb->tma_ok = false;
+    if (ctx->encode && width % 4 == 0) {
+        int r1 = make_tensor_map(ctx, &rb->tm_color, CU_TENSOR_MAP_DATA_TYPE_UINT32, 4, rb->color, width, height, 1,
+                                 (uint64_t)width * 4, (uint64_t)n * 4);
+        int r2 = make_tensor_map(ctx, &rb->tm_depth, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, rb->depth, width, height, 1,
+                                 (uint64_t)width * 4, (uint64_t)n * 4);
+        rb->tma_ok = (r1 == HANA_OK && r2 == HANA_OK);
+    }
+    /* RenderBuffer ctor: colour (0,0,0,255), depth 1.0 (renderbuffer.cpp:6-7,16-17) */
+    HANA_TRY(launch_fill32(ctx, rb->color, 0xFF000000u, n));
+    float one = 1.0f;
+    uint32_t bits;
+    memcpy(&bits, &one, 4);
+    HANA_TRY(launch_fill32(ctx, reinterpret_cast<uint32_t*>(rb->depth), bits, n));
+    *out = rb;
+    return HANA_OK;
+}
+extern "C" int hana_rb_destroy(hana_rb* rb) {
+    if (!rb) return HANA_OK;
+    cudaSetDevice(rb->ctx->device);
+    cudaStreamSynchronize(rb->ctx->stream);
+    cudaFree(rb->color);
+    cudaFree(rb->depth);
+    delete rb;
+    return HANA_OK;
+}
+extern "C" int hana_rb_size(const hana_rb* rb, int* width, int* height) {
+    if (!rb) return fail(HANA_E_INVALID, "rb is NULL");
+    if (width) *width = rb->w;
+    if (height) *height = rb->h;
+    return HANA_OK;
+}
+extern "C" int hana_rb_clear_color(hana_rb* rb, uint8_t r, uint8_t g, uint8_t b, uint8_t a) {
+    if (!rb) return fail(HANA_E_INVALID, "rb is NULL");
+    HANA_TRY(use_device(rb->ctx));
+    uint32_t v = (uint32_t)r | ((uint32_t)g << 8) | ((uint32_t)b << 16) | ((uint32_t)a << 24);
+    return launch_fill32(rb->ctx, rb->color, v, (size_t)rb->w * rb->h);
+}
+extern "C" int hana_rb_clear_depth(hana_rb* rb, float depth) {
+    if (!rb) return fail(HANA_E_INVALID, "rb is NULL");
+    HANA_TRY(use_device(rb->ctx));
+    uint32_t bits;
+    memcpy(&bits, &depth, 4);
+    return launch_fill32(rb->ctx, reinterpret_cast<uint32_t*>(rb->depth), bits, (size_t)rb->w * rb->h);
+}
+extern "C" int hana_rb_upload(hana_rb* rb, const uint8_t* color_rgba, const float* depth) {
+    if (!rb) return fail(HANA_E_INVALID, "rb is NULL");
+    HANA_TRY(use_device(rb->ctx));
+    size_t n = (size_t)rb->w * rb->h * 4;
+    if (color_rgba) CU_TRY(cudaMemcpyAsync(rb->color, color_rgba, n, cudaMemcpyHostToDevice, rb->ctx->stream));
+    if (depth) CU_TRY(cudaMemcpyAsync(rb->depth, depth, n, cudaMemcpyHostToDevice, rb->ctx->stream));
+    CU_TRY(cudaStreamSynchronize(rb->ctx->stream));
+    return HANA_OK;
+}
+extern "C" int hana_rb_download(hana_rb* rb, uint8_t* color_rgba, float* depth) {
+    if (!rb) return fail(HANA_E_INVALID, "rb is NULL");
+    HANA_TRY(use_device(rb->ctx));
+    size_t n = (size_t)rb->w * rb->h * 4;
+    if (color_rgba) CU_TRY(cudaMemcpyAsync(color_rgba, rb->color, n, cudaMemcpyDeviceToHost, rb->ctx->stream));
+    if (depth) CU_TRY(cudaMemcpyAsync(depth, rb->depth, n, cudaMemcpyDeviceToHost, rb->ctx->stream));
+    CU_TRY(cudaStreamSynchronize(rb->ctx->stream));
+    return HANA_OK;
+}
+extern "C" int hana_rb_device_ptrs(hana_rb* rb, void** color_dev, void** depth_dev) {
+    if (!rb) return fail(HANA_E_INVALID, "rb is NULL");
+    if (color_dev) *color_dev = rb->color;
+    if (depth_dev) *depth_dev = rb->depth;
+    return HANA_OK;
+}
+
+/* ---- one pass -------------------------------------------------------------------- */
+struct PassDesc {
+    int shader = 0, mode = MODE_RMW, n_frames = 1, W = 0, H = 0;
+    const hana_model* model = nullptr;
+    const DevUniforms* uniforms = nullptr;
+    uint32_t* color = nullptr;
+    float* depth = nullptr;
+    size_t frame_stride = 0;
+    const CUtensorMap* tm_color = nullptr;
+    const CUtensorMap* tm_depth = nullptr;
+    const CUtensorMap* tm_r8 = nullptr;
+    bool tma_ok = false;
+    uint8_t* shadow_out = nullptr;
+    int shadow_out_pitch = 0;
+    size_t shadow_out_frame_stride = 0;
+    uint32_t clear_color = 0;
+    float clear_depth = 0.f;
+    DevTexture diffuse{nullptr, 0, 0}, normal{nullptr, 0, 0};
+    DevShadow shadow{nullptr, 0, 0, 0, 0};
+    size_t shadow_frame_stride = 0;
+    uint32_t* primid = nullptr;
+    uint32_t* pixels_covered = nullptr;
+    float* dbg_v2f = nullptr;
+    uint32_t dbg_cap = 0;
+    bool setup_only = false;
+    int prof_kind = PROF_RASTER_MAIN;
+    std::vector<uint32_t>* tri_counts_out = nullptr;
+    PassCounters* counters_out = nullptr;
+};
+
+template <typename T>
+static int grow(T** ptr, size_t* cap, size_t need, hana_ctx* ctx) {
+    if (need <= *cap && *ptr) return HANA_OK;
+    size_t n = std::max(need, *cap + *cap / 2);
+    n = std::max<size_t>(n, 1);
+    CU_TRY(cudaStreamSynchronize(ctx->stream));
+    if (*ptr) CU_TRY(cudaFree(*ptr));
+    *ptr = nullptr;
+    *cap = 0;
+    CU_TRY(cudaMalloc(ptr, n * sizeof(T)));
+    *cap = n;
+    return HANA_OK;
+}
+
+template <int MODE>
+static int launch_raster(hana_ctx* ctx, int shader, int blocks, const RasterParams& rp, const CUtensorMap& a,
+                         const CUtensorMap& b, const CUtensorMap& c) {
+#define HANA_RASTER_CASE(S) \
+    case S: raster_kernel<S, MODE><<<blocks, RASTER_THREADS, 0, ctx->stream>>>(rp, a, b, c); break;
+    switch (shader) {
+        HANA_RASTER_CASE(HANA_SHADER_SHADOW)
+        HANA_RASTER_CASE(HANA_SHADER_BLINN)
+        HANA_RASTER_CASE(HANA_SHADER_NORMALMAP)
+        HANA_RASTER_CASE(HANA_SHADER_GROUND)
+        HANA_RASTER_CASE(HANA_SHADER_TOON)
+        HANA_RASTER_CASE(HANA_SHADER_TEXTURE)
+        HANA_RASTER_CASE(HANA_SHADER_TEXTURE_LIGHT)
+        default: return fail(HANA_E_UNSUPPORTED, "unknown shader id");
+    }
+#undef HANA_RASTER_CASE
+    return HANA_OK;
+}
+
+template <int MODE>
+static int raster_occupancy(int shader) {
+    int occ = 0;
+#define HANA_OCC_CASE(S) \
+    case S: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, raster_kernel<S, MODE>, RASTER_THREADS, 0); break;
+    switch (shader) {
+        HANA_OCC_CASE(HANA_SHADER_SHADOW)
+        HANA_OCC_CASE(HANA_SHADER_BLINN)
+        HANA_OCC_CASE(HANA_SHADER_NORMALMAP)
+        HANA_OCC_CASE(HANA_SHADER_GROUND)
+        HANA_OCC_CASE(HANA_SHADER_TOON)
+        HANA_OCC_CASE(HANA_SHADER_TEXTURE)
+        HANA_OCC_CASE(HANA_SHADER_TEXTURE_LIGHT)
+    }
+#undef HANA_OCC_CASE
+    return occ;
+}
+
+static int run_pass(hana_ctx* ctx, const PassDesc& d) {
+    if (d.shader < 0 || d.shader >= HANA_SHADER_COUNT) return fail(HANA_E_UNSUPPORTED, "unknown shader id");
+    if (d.mode == MODE_SHADOW_R8 && d.shader != HANA_SHADER_SHADOW)
+        return fail(HANA_E_INVALID, "R8 targets take the ShadowShader only");
+    const int tiles_x = (d.W + TILE - 1) / TILE, tiles_y = (d.H + TILE - 1) / TILE;
+    const size_t n_tiles = (size_t)tiles_x * tiles_y;
+    if (n_tiles > TILE_MASK) return fail(HANA_E_INVALID, "too many screen tiles");
+    if (d.n_frames < 1 || d.n_frames > 4096) return fail(HANA_E_INVALID, "1..4096 frames per batch");
+    const int nfaces = d.model->ncorners / 3;
+    Scratch& sc = ctx->sc;
+    const size_t tiles_total = n_tiles * d.n_frames;
+    if (tiles_total > 0xFFFFFFF0ull) return fail(HANA_E_INVALID, "frames x tiles exceeds 32 bits");
+
+    uint32_t tri_cap = std::max<uint32_t>(ctx->tri_cap_hint, (uint32_t)(nfaces + nfaces / 8 + 64));
+    if (d.dbg_v2f) tri_cap = std::min(tri_cap, std::max<uint32_t>(d.dbg_cap, 1u));
+    PassParams p;
+    memset(&p, 0, sizeof(p));
+    RasterParams rp;
+    bool lists_ready = false;
+    for (int attempt = 0; attempt < 4 && !lists_ready; attempt++) {
+        /* capacities */
+        size_t tri_total = (size_t)tri_cap * d.n_frames;
+        HANA_TRY(grow(&sc.tri_rec, &sc.tri_total, tri_total, ctx));
+        HANA_TRY(grow(&sc.tri_attr, &sc.attr_total, tri_total * 6, ctx));
+        HANA_TRY(grow(&sc.tri_count, &sc.frames_cap, (size_t)d.n_frames, ctx));
+        HANA_TRY(grow(&sc.tile_arrays, &sc.tile_arr_cap, tiles_total * 3, ctx));
+        HANA_TRY(grow(&sc.work, &sc.work_cap, tiles_total, ctx));
+        if (!sc.refs) HANA_TRY(grow(&sc.refs, &sc.pool_cap, std::max<size_t>(tri_total * 8, 65536), ctx));
+
+        p.posu = d.model->posu;
+        p.nrmv = d.model->nrmv;
+        p.nfaces = nfaces;
+        p.n_frames = d.n_frames;
+        p.W = d.W;
+        p.H = d.H;
+        p.tiles_x = tiles_x;
+        p.tiles_y = tiles_y;
+        p.n_tiles = (int)n_tiles;
+        p.uniforms = d.uniforms;
+        p.tri_rec = sc.tri_rec;
+        p.tri_attr = sc.tri_attr;
+        p.tri_cap = tri_cap;
+        p.tri_count = sc.tri_count;
+        p.tile_count = sc.tile_arrays;
+        p.tile_cursor = sc.tile_arrays + tiles_total;
+        p.tile_offset = sc.tile_arrays + 2 * tiles_total;
+        p.refs = sc.refs;
+        p.pool_cap = (uint32_t)std::min<size_t>(sc.pool_cap, 0xFFFFFFFFull);
+        p.work = sc.work;
+        p.counters = sc.counters;
+        p.dbg_v2f = d.dbg_v2f;
+
+        /* zero: counters, per-frame triangle counts, tile counts + cursors (contiguous) */
+        CU_TRY(cudaMemsetAsync(sc.counters, 0, sizeof(PassCounters), ctx->stream));
+        CU_TRY(cudaMemsetAsync(sc.tri_count, 0, sizeof(uint32_t) * d.n_frames, ctx->stream));
+        CU_TRY(cudaMemsetAsync(sc.tile_arrays, 0, sizeof(uint32_t) * 2 * tiles_total, ctx->stream));
+
+        cudaEvent_t ea, eb;
+        if (nfaces > 0) {
+            dim3 grid((nfaces + SETUP_THREADS - 1) / SETUP_THREADS, d.n_frames);
+            prof_begin(ctx, PROF_SETUP, &ea, &eb);
+#define HANA_SETUP_CASE(S) \
+    case S: setup_kernel<S><<<grid, SETUP_THREADS, 0, ctx->stream>>>(p); break;
+            switch (d.shader) {
+                HANA_SETUP_CASE(HANA_SHADER_SHADOW)
+                HANA_SETUP_CASE(HANA_SHADER_BLINN)
+                HANA_SETUP_CASE(HANA_SHADER_NORMALMAP)
+                HANA_SETUP_CASE(HANA_SHADER_GROUND)
+                HANA_SETUP_CASE(HANA_SHADER_TOON)
+                HANA_SETUP_CASE(HANA_SHADER_TEXTURE)
+                HANA_SETUP_CASE(HANA_SHADER_TEXTURE_LIGHT)
+            }
+#undef HANA_SETUP_CASE
+            prof_end(ctx, PROF_SETUP, ea, eb);
+            ctx->launches++;
+            CU_TRY(cudaGetLastError());
+        }
+        prof_begin(ctx, PROF_SCAN, &ea, &eb);
+        scan_kernel<<<d.n_frames, SCAN_THREADS, 0, ctx->stream>>>(p);
+        prof_end(ctx, PROF_SCAN, ea, eb);
+        ctx->launches++;
+        CU_TRY(cudaGetLastError());
+        CU_TRY(cudaMemcpyAsync(sc.counters_host, sc.counters, sizeof(PassCounters), cudaMemcpyDeviceToHost, ctx->stream));
+        CU_TRY(cudaStreamSynchronize(ctx->stream));
+        const PassCounters& c = *sc.counters_host;
+        if (c.tri_needed > tri_cap) {
+            if (d.dbg_v2f) return fail(HANA_E_OVERFLOW, "stage output capacity too small: " + std::to_string(c.tri_needed));
+            tri_cap = c.tri_needed + c.tri_needed / 8 + 64;
+            ctx->tri_cap_hint = std::max(ctx->tri_cap_hint, tri_cap);
+            continue; /* triangles were dropped: redo setup with room for all of them */
+        }
+        if ((size_t)c.pool_used > sc.pool_cap) {
+            HANA_TRY(grow(&sc.refs, &sc.pool_cap, (size_t)c.pool_used + c.pool_used / 8, ctx));
+            p.refs = sc.refs;
+            p.pool_cap = (uint32_t)std::min<size_t>(sc.pool_cap, 0xFFFFFFFFull);
+        }
+        lists_ready = true;
+    }
+    if (!lists_ready) return fail(HANA_E_OVERFLOW, "triangle capacity still exceeded after retries");
+    const PassCounters cnt = *sc.counters_host;
+    if (d.counters_out) *d.counters_out = cnt;
+    if (d.tri_counts_out) {
+        d.tri_counts_out->resize(d.n_frames);
+        CU_TRY(cudaMemcpyAsync(d.tri_counts_out->data(), sc.tri_count, sizeof(uint32_t) * d.n_frames, cudaMemcpyDeviceToHost,
+                               ctx->stream));
+        CU_TRY(cudaStreamSynchronize(ctx->stream));
+    }
+    if (d.setup_only) return HANA_OK;
+
+    cudaEvent_t ea, eb;
+    if (cnt.pool_used > 0) {
+        dim3 grid((std::min(cnt.tri_needed, tri_cap) + 255) / 256, d.n_frames);
+        if (grid.x > 0) {
+            prof_begin(ctx, PROF_FILL, &ea, &eb);
+            fill_kernel<<<grid, 256, 0, ctx->stream>>>(p);
+            prof_end(ctx, PROF_FILL, ea, eb);
+            ctx->launches++;
+            CU_TRY(cudaGetLastError());
+        }
+    }
+    if (d.mode == MODE_RMW && cnt.n_work == 0) return HANA_OK; /* nothing covers anything */
+
+    memset(&rp, 0, sizeof(rp));
+    rp.p = p;
+    rp.color = d.color;
+    rp.depth = d.depth;
+    rp.frame_stride = d.frame_stride;
+    rp.shadow_out = d.shadow_out;
+    rp.shadow_out_pitch = d.shadow_out_pitch;
+    rp.shadow_out_frame_stride = d.shadow_out_frame_stride;
+    rp.clear_color = d.clear_color;
+    rp.clear_depth = d.clear_depth;
+    rp.use_tma = (ctx->use_tma && d.tma_ok) ? 1 : 0;
+    rp.diffuse = d.diffuse;
+    rp.normal = d.normal;
+    rp.shadow = d.shadow;
+    rp.shadow_frame_stride = d.shadow_frame_stride;
+    rp.primid = d.primid;
+    rp.pixels_covered = d.pixels_covered;
+
+    int& occ = ctx->occ[d.shader][d.mode];
+    if (occ == 0) {
+        occ = d.mode == MODE_CLEAR_FOLD ? raster_occupancy<MODE_CLEAR_FOLD>(d.shader)
+              : d.mode == MODE_RMW      ? raster_occupancy<MODE_RMW>(d.shader)
+                                        : raster_occupancy<MODE_SHADOW_R8>(HANA_SHADER_SHADOW);
+        cudaGetLastError();
+        if (occ <= 0) occ = 1;
+    }
+    size_t want = cnt.n_work;
+    if (d.mode != MODE_RMW) want = std::max<size_t>(want, (tiles_total + 255) / 256);
+    int blocks = (int)std::max<size_t>(1, std::min<size_t>(want, (size_t)ctx->sm_count * occ));
+    static const CUtensorMap dummy = {};
+    const CUtensorMap& ta = d.tm_color ? *d.tm_color : dummy;
+    const CUtensorMap& tb = d.tm_depth ? *d.tm_depth : dummy;
+    const CUtensorMap& tc = d.tm_r8 ? *d.tm_r8 : dummy;
+    prof_begin(ctx, d.prof_kind, &ea, &eb);
+    int r = d.mode == MODE_CLEAR_FOLD ? launch_raster<MODE_CLEAR_FOLD>(ctx, d.shader, blocks, rp, ta, tb, tc)
+            : d.mode == MODE_RMW      ? launch_raster<MODE_RMW>(ctx, d.shader, blocks, rp, ta, tb, tc)
+                                      : launch_raster<MODE_SHADOW_R8>(ctx, HANA_SHADER_SHADOW, blocks, rp, ta, tb, tc);
+    prof_end(ctx, d.prof_kind, ea, eb);
+    HANA_TRY(r);
+    ctx->launches++;
+    CU_TRY(cudaGetLastError());
+    return HANA_OK;
+}
+
+static int upload_uniforms(hana_ctx* ctx, const HanaUniforms* host, int n, HanaUniforms* raw_dev, DevUniforms* dev) {
+    if (host) CU_TRY(cudaMemcpyAsync(raw_dev, host, sizeof(HanaUniforms) * n, cudaMemcpyHostToDevice, ctx->stream));
+    cudaEvent_t a, b;
+    prof_begin(ctx, PROF_BEGIN, &a, &b);
+    begin_kernel<<<(n + 63) / 64, 64, 0, ctx->stream>>>(raw_dev, dev, n);
+    prof_end(ctx, PROF_BEGIN, a, b);
+    ctx->launches++;
+    CU_TRY(cudaGetLastError());
+    return HANA_OK;
+}
+
+static DevTexture dev_tex(const hana_texture* t) {
+    DevTexture d{nullptr, 0, 0};
+    if (t) {
+        d.texels = t->texels;
+        d.w = t->w;
+        d.h = t->h;
+    }
+    return d;
+}
+
+/* graphics_draw_triangle (graphics.cpp:378-407) into an existing target. */
+static int draw_rmw(hana_ctx* ctx, hana_rb* rb, const hana_model* model, int shader, const hana_texture* diffuse,
+                    const hana_texture* normal, const hana_rb* shadow_map, uint32_t* primid_dev, bool want_stats) {
+    PassDesc d;
+    d.shader = shader;
+    d.mode = MODE_RMW;
+    d.n_frames = 1;
+    d.W = rb->w;
+    d.H = rb->h;
+    d.model = model;
+    d.uniforms = ctx->u_dev;
+    d.color = rb->color;
+    d.depth = rb->depth;
+    d.frame_stride = (size_t)rb->w * rb->h;
+    d.tm_color = &rb->tm_color;
+    d.tm_depth = &rb->tm_depth;
+    d.tma_ok = rb->tma_ok;
+    d.diffuse = dev_tex(diffuse);
+    d.normal = dev_tex(normal);
+    if (shadow_map) {
+        d.shadow.base = reinterpret_cast<const uint8_t*>(shadow_map->color);
+        d.shadow.w = shadow_map->w;
+        d.shadow.h = shadow_map->h;
+        d.shadow.pitch = shadow_map->w * 4;
+        d.shadow.stride = 4;
+    }
+    d.primid = primid_dev;
+    d.prof_kind = shader == HANA_SHADER_SHADOW ? PROF_RASTER_SHADOW : PROF_RASTER_MAIN;
+    PassCounters cnt;
+    std::vector<uint32_t> tri_counts;
+    d.counters_out = &cnt;
+    d.tri_counts_out = &tri_counts;
+    if (want_stats) {
+        CU_TRY(cudaMemsetAsync(ctx->stat_pixels, 0, 4, ctx->stream));
+        d.pixels_covered = ctx->stat_pixels;
+    }
+    HANA_TRY(run_pass(ctx, d));
+    HanaStats& s = ctx->last_stats;
+    memset(&s, 0, sizeof(s));
+    s.faces_in = (uint32_t)(model->ncorners / 3);
+    s.tris_out = tri_counts.empty() ? 0 : tri_counts[0];
+    s.tile_refs = cnt.pool_used;
+    s.tiles_touched = cnt.tiles_touched;
+    return HANA_OK;
+}
+
+static int check_draw_args(hana_ctx* ctx, const hana_model* model, const HanaUniforms* u, int shader) {
+    if (!ctx || !model || !u) return fail(HANA_E_INVALID, "NULL argument");
+    if (model->ctx != ctx) return fail(HANA_E_INVALID, "model belongs to another context");
+    if (shader < 0 || shader >= HANA_SHADER_COUNT)
+        return fail(HANA_E_UNSUPPORTED, "shader id outside the closed device set (IShader subclasses cannot run on the device)");
+    return HANA_OK;
+}
+
+extern "C" int hana_draw(hana_ctx* ctx, hana_rb* rb, const hana_model* model, int shader_id, const HanaUniforms* uniforms,
+                         const hana_texture* diffuse, const hana_texture* normal, const hana_rb* shadow_map) {
+    HANA_TRY(check_draw_args(ctx, model, uniforms, shader_id));
+    if (!rb) return fail(HANA_E_INVALID, "rb is NULL");
+    HANA_TRY(use_device(ctx));
+    HANA_TRY(upload_uniforms(ctx, uniforms, 1, ctx->u_raw, ctx->u_dev));
+    return draw_rmw(ctx, rb, model, shader_id, diffuse, normal, uniforms->enable_shadow ? shadow_map : nullptr, nullptr, true);
+}
+
+extern "C" int hana_draw_primid(hana_ctx* ctx, hana_rb* rb, const hana_model* model, int shader_id,
+                                const HanaUniforms* uniforms, const hana_texture* diffuse, const hana_texture* normal,
+                                const hana_rb* shadow_map, uint32_t* out_primid_host) {
+    HANA_TRY(check_draw_args(ctx, model, uniforms, shader_id));
+    if (!rb || !out_primid_host) return fail(HANA_E_INVALID, "NULL argument");
+    HANA_TRY(use_device(ctx));
+    size_t n = (size_t)rb->w * rb->h;
+    uint32_t* pid = nullptr;
+    CU_TRY(cudaMalloc(&pid, n * 4));
+    int r = launch_fill32(ctx, pid, 0xFFFFFFFFu, n);
+    if (r == HANA_OK) r = upload_uniforms(ctx, uniforms, 1, ctx->u_raw, ctx->u_dev);
+    if (r == HANA_OK)
+        r = draw_rmw(ctx, rb, model, shader_id, diffuse, normal, uniforms->enable_shadow ? shadow_map : nullptr, pid, true);
+    if (r == HANA_OK) {
+        cudaError_t e = cudaMemcpyAsync(out_primid_host, pid, n * 4, cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) r = fail(HANA_E_CUDA, cudaGetErrorString(e));
+    }
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(pid);
+    return r;
+}
+
+extern "C" int hana_draw_model(hana_ctx* ctx, hana_rb* frame, hana_rb* shadow_map, const hana_model* model, int shader_id,
+                               const HanaUniforms* uniforms, const hana_texture* diffuse, const hana_texture* normal) {
+    HANA_TRY(check_draw_args(ctx, model, uniforms, shader_id));
+    if (!frame) return fail(HANA_E_INVALID, "frame is NULL");
+    if (uniforms->enable_shadow && !shadow_map) return fail(HANA_E_INVALID, "enable_shadow needs a shadow map target");
+    HANA_TRY(use_device(ctx));
+    HANA_TRY(upload_uniforms(ctx, uniforms, 1, ctx->u_raw, ctx->u_dev));
+    if (uniforms->enable_shadow) { /* scene.h:73-88 */
+        HANA_TRY(draw_rmw(ctx, shadow_map, model, HANA_SHADER_SHADOW, nullptr, nullptr, nullptr, nullptr, false));
+    }
+    HANA_TRY(draw_rmw(ctx, frame, model, shader_id, diffuse, normal, uniforms->enable_shadow ? shadow_map : nullptr, nullptr,
+                      true)); /* scene.h:90-91 */
+    if (uniforms->enable_shadow) { /* scene.h:94-98: Color::Black has a = 255 -> (uchar)(255*255) -> 1 on x86-64 (App. D5) */
+        HANA_TRY(hana_rb_clear_color(shadow_map, 0, 0, 0, 1));
+        HANA_TRY(hana_rb_clear_depth(shadow_map, 3.402823466e+38f));
+    }
+    return HANA_OK;
+}
+
+extern "C" int hana_last_stats(hana_ctx* ctx, HanaStats* out) {
+    if (!ctx || !out) return fail(HANA_E_INVALID, "NULL argument");
+    HANA_TRY(use_device(ctx));
+    CU_TRY(cudaStreamSynchronize(ctx->stream));
+    uint32_t px = 0;
+    CU_TRY(cudaMemcpy(&px, ctx->stat_pixels, 4, cudaMemcpyDeviceToHost));
+    ctx->last_stats.pixels_covered = px;
+    *out = ctx->last_stats;
+    return HANA_OK;
+}
+
+/* ---- batched sweep ------------------------------------------------------------------ */
+extern "C" int hana_sweep_create(hana_ctx* ctx, int width, int height, int max_frames, hana_sweep** out) {
+    if (!ctx || !out) return fail(HANA_E_INVALID, "NULL argument");
+    if (width <= 0 || height <= 0 || width > 65535 || height > 65535 || max_frames < 1 || max_frames > 4096)
+        return fail(HANA_E_INVALID, "sweep size out of range");
+    HANA_TRY(use_device(ctx));
+    hana_sweep* s = new hana_sweep();
+    s->ctx = ctx;
+    s->w = width;
+    s->h = height;
+    s->max_frames = max_frames;
+    s->last_frames = 0;
+    s->last_clear_depth = 0.f;
+    memset(&s->last_stats, 0, sizeof(s->last_stats));
+    size_t n = (size_t)width * height;
+    s->shadow_pitch = (width + 15) / 16 * 16;
+    s->shadow_frame_bytes = (size_t)s->shadow_pitch * ((height + 15) / 16 * 16);
+    s->color = nullptr; s->depth = nullptr; s->shadow_r8 = nullptr; s->u_raw = nullptr; s->u_dev = nullptr;
+    s->checksums = nullptr; s->pix_counts = nullptr;
+    cudaError_t e = cudaMalloc(&s->color, n * 4 * max_frames);
+    if (e == cudaSuccess) e = cudaMalloc(&s->depth, n * 4 * max_frames);
+    if (e == cudaSuccess) e = cudaMalloc(&s->shadow_r8, s->shadow_frame_bytes * max_frames);
+    if (e == cudaSuccess) e = cudaMalloc(&s->u_raw, sizeof(HanaUniforms) * max_frames);
+    if (e == cudaSuccess) e = cudaMalloc(&s->u_dev, sizeof(DevUniforms) * max_frames);
+    if (e == cudaSuccess) e = cudaMalloc(&s->checksums, sizeof(unsigned long long) * max_frames);
+    if (e == cudaSuccess) e = cudaMalloc(&s->pix_counts, sizeof(uint32_t) * max_frames);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        hana_sweep_destroy(s);
+        return fail(HANA_E_CUDA, std::string("cudaMalloc failed for the frame ring: ") + cudaGetErrorString(e));
+    }
+    s->tma_ok = false;
+    if (ctx->encode && width % 4 == 0) {
+        int r1 = make_tensor_map(ctx, &s->tm_color, CU_TENSOR_MAP_DATA_TYPE_UINT32, 4, s->color, width, height, max_frames,
+                                 (uint64_t)width * 4, (uint64_t)n * 4);
+        int r2 = make_tensor_map(ctx, &s->tm_depth, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, s->depth, width, height, max_frames,
+                                 (uint64_t)width * 4, (uint64_t)n * 4);
+        int r3 = make_tensor_map(ctx, &s->tm_r8, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, s->shadow_r8, width, height, max_frames,
+                                 (uint64_t)s->shadow_pitch, (uint64_t)s->shadow_frame_bytes);
+        s->tma_ok = (r1 == HANA_OK && r2 == HANA_OK && r3 == HANA_OK);
+    }
+    *out = s;
+    return HANA_OK;
+}
+extern "C" int hana_sweep_destroy(hana_sweep* s) {
+    if (!s) return HANA_OK;
+    cudaSetDevice(s->ctx->device);
+    cudaStreamSynchronize(s->ctx->stream);
+    cudaFree(s->color); cudaFree(s->depth); cudaFree(s->shadow_r8); cudaFree(s->u_raw); cudaFree(s->u_dev);
+    cudaFree(s->checksums); cudaFree(s->pix_counts);
+    if (s->ctx->host_sweep == s) s->ctx->host_sweep = nullptr;
+    delete s;
+    return HANA_OK;
+}
+
+static int sweep_render_common(hana_sweep* s, const hana_model* model, int shader_id, const HanaUniforms* host_uniforms,
+                               int enable_shadow, int n_frames, const hana_texture* diffuse, const hana_texture* normal,
+                               const uint8_t clear_rgba[4], float clear_depth) {
+    hana_ctx* ctx = s->ctx;
+    HANA_TRY(upload_uniforms(ctx, host_uniforms, n_frames, s->u_raw, s->u_dev));
+    PassCounters cnt[2];
+    memset(cnt, 0, sizeof(cnt));
+    if (enable_shadow) { /* scene.h:73-88, into the internal R8 maps */
+        PassDesc d;
+        d.shader = HANA_SHADER_SHADOW;
+        d.mode = MODE_SHADOW_R8;
+        d.n_frames = n_frames;
+        d.W = s->w;
+        d.H = s->h;
+        d.model = model;
+        d.uniforms = s->u_dev;
+        d.tm_r8 = &s->tm_r8;
+        d.tma_ok = s->tma_ok;
+        d.shadow_out = s->shadow_r8;
+        d.shadow_out_pitch = s->shadow_pitch;
+        d.shadow_out_frame_stride = s->shadow_frame_bytes;
+        d.clear_depth = 3.402823466e+38f; /* scene.h:97 */
+        d.prof_kind = PROF_RASTER_SHADOW;
+        d.counters_out = &cnt[0];
+        d.tri_counts_out = &s->last_tri_counts[0];
+        HANA_TRY(run_pass(ctx, d));
+    }
+    PassDesc d;
+    d.shader = shader_id;
+    d.mode = MODE_CLEAR_FOLD;
+    d.n_frames = n_frames;
+    d.W = s->w;
+    d.H = s->h;
+    d.model = model;
+    d.uniforms = s->u_dev;
+    d.color = s->color;
+    d.depth = s->depth;
+    d.frame_stride = (size_t)s->w * s->h;
+    d.tm_color = &s->tm_color;
+    d.tm_depth = &s->tm_depth;
+    d.tma_ok = s->tma_ok;
+    d.clear_color = (uint32_t)clear_rgba[0] | ((uint32_t)clear_rgba[1] << 8) | ((uint32_t)clear_rgba[2] << 16) |
+                    ((uint32_t)clear_rgba[3] << 24);
+    d.clear_depth = clear_depth;
+    d.diffuse = dev_tex(diffuse);
+    d.normal = dev_tex(normal);
+    if (enable_shadow) {
+        d.shadow.base = s->shadow_r8;
+        d.shadow.w = s->w;
+        d.shadow.h = s->h;
+        d.shadow.pitch = s->shadow_pitch;
+        d.shadow.stride = 1;
+        d.shadow_frame_stride = s->shadow_frame_bytes;
+    }
+    d.prof_kind = PROF_RASTER_MAIN;
+    d.counters_out = &cnt[1];
+    d.tri_counts_out = &s->last_tri_counts[1];
+    HANA_TRY(run_pass(ctx, d));
+    s->last_frames = n_frames;
+    s->last_clear_depth = clear_depth;
+    memset(&s->last_stats, 0, sizeof(s->last_stats));
+    s->last_stats.faces_in = (uint32_t)(model->ncorners / 3);
+    s->last_stats.tile_refs = cnt[1].pool_used;
+    s->last_stats.tiles_touched = cnt[1].tiles_touched;
+    return HANA_OK;
+}
+
+extern "C" int hana_sweep_render(hana_sweep* s, const hana_model* model, int shader_id, const HanaUniforms* uniforms,
+                                 int n_frames, const hana_texture* diffuse, const hana_texture* normal,
+                                 const uint8_t clear_rgba[4], float clear_depth) {
+    if (!s) return fail(HANA_E_INVALID, "sweep is NULL");
+    HANA_TRY(check_draw_args(s->ctx, model, uniforms, shader_id));
+    if (!clear_rgba) return fail(HANA_E_INVALID, "clear_rgba is NULL");
+    if (n_frames < 1 || n_frames > s->max_frames) return fail(HANA_E_INVALID, "n_frames outside 1..max_frames");
+    for (int i = 1; i < n_frames; i++)
+        if ((uniforms[i].enable_shadow != 0) != (uniforms[0].enable_shadow != 0))
+            return fail(HANA_E_INVALID, "all frames of a batch must agree on enable_shadow");
+    HANA_TRY(use_device(s->ctx));
+    return sweep_render_common(s, model, shader_id, uniforms, uniforms[0].enable_shadow != 0, n_frames, diffuse, normal,
+                               clear_rgba, clear_depth);
+}
+
+extern "C" int hana_sweep_render_dev(hana_sweep* s, const hana_model* model, int shader_id, const void* uniforms_dev,
+                                     int n_frames, const hana_texture* diffuse, const hana_texture* normal,
+                                     const uint8_t clear_rgba[4], float clear_depth) {
+    if (!s || !uniforms_dev || !model || !clear_rgba) return fail(HANA_E_INVALID, "NULL argument");
+    if (model->ctx != s->ctx) return fail(HANA_E_INVALID, "model belongs to another context");
+    if (shader_id < 0 || shader_id >= HANA_SHADER_COUNT) return fail(HANA_E_UNSUPPORTED, "shader id outside the device set");
+    if (n_frames < 1 || n_frames > s->max_frames) return fail(HANA_E_INVALID, "n_frames outside 1..max_frames");
+    hana_ctx* ctx = s->ctx;
+    HANA_TRY(use_device(ctx));
+    if (uniforms_dev != s->u_raw)
+        CU_TRY(cudaMemcpyAsync(s->u_raw, uniforms_dev, sizeof(HanaUniforms) * n_frames, cudaMemcpyDeviceToDevice, ctx->stream));
+    int32_t enable = 0; /* frame 0 decides for the batch */
+    CU_TRY(cudaMemcpyAsync(&enable, reinterpret_cast<const char*>(s->u_raw) + offsetof(HanaUniforms, enable_shadow), 4,
+                           cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(cudaStreamSynchronize(ctx->stream));
+    return sweep_render_common(s, model, shader_id, nullptr, enable != 0, n_frames, diffuse, normal, clear_rgba, clear_depth);
+}
+
+extern "C" int hana_sweep_uniforms_dev(hana_sweep* s, void** out) {
+    if (!s || !out) return fail(HANA_E_INVALID, "NULL argument");
+    *out = s->u_raw;
+    return HANA_OK;
+}
+
+extern "C" int hana_sweep_download(hana_sweep* s, int frame, uint8_t* color_rgba, float* depth) {
+    if (!s) return fail(HANA_E_INVALID, "sweep is NULL");
+    if (frame < 0 || frame >= s->max_frames) return fail(HANA_E_INVALID, "frame out of range");
+    HANA_TRY(use_device(s->ctx));
+    size_t n = (size_t)s->w * s->h;
+    if (color_rgba)
+        CU_TRY(cudaMemcpyAsync(color_rgba, s->color + n * frame, n * 4, cudaMemcpyDeviceToHost, s->ctx->stream));
+    if (depth) CU_TRY(cudaMemcpyAsync(depth, s->depth + n * frame, n * 4, cudaMemcpyDeviceToHost, s->ctx->stream));
+    CU_TRY(cudaStreamSynchronize(s->ctx->stream));
+    return HANA_OK;
+}
+extern "C" int hana_sweep_download_async(hana_sweep* s, int first, int count, uint8_t* color_rgba_pinned, float* depth_pinned) {
+    if (!s) return fail(HANA_E_INVALID, "sweep is NULL");
+    if (first < 0 || count < 0 || first + count > s->max_frames) return fail(HANA_E_INVALID, "frame range out of bounds");
+    HANA_TRY(use_device(s->ctx));
+    size_t n = (size_t)s->w * s->h;
+    if (color_rgba_pinned)
+        CU_TRY(cudaMemcpyAsync(color_rgba_pinned, s->color + n * first, n * 4 * count, cudaMemcpyDeviceToHost, s->ctx->stream));
+    if (depth_pinned)
+        CU_TRY(cudaMemcpyAsync(depth_pinned, s->depth + n * first, n * 4 * count, cudaMemcpyDeviceToHost, s->ctx->stream));
+    return HANA_OK;
+}
+extern "C" int hana_sweep_device_ptrs(hana_sweep* s, void** color_dev, void** depth_dev, size_t* frame_stride_pixels) {
+    if (!s) return fail(HANA_E_INVALID, "sweep is NULL");
+    if (color_dev) *color_dev = s->color;
+    if (depth_dev) *depth_dev = s->depth;
+    if (frame_stride_pixels) *frame_stride_pixels = (size_t)s->w * s->h;
+    return HANA_OK;
+}
+extern "C" int hana_sweep_checksums(hana_sweep* s, int n_frames, uint64_t* out_host) {
+    if (!s || !out_host) return fail(HANA_E_INVALID, "NULL argument");
+    if (n_frames < 1 || n_frames > s->max_frames) return fail(HANA_E_INVALID, "n_frames out of range");
+    hana_ctx* ctx = s->ctx;
+    HANA_TRY(use_device(ctx));
+    CU_TRY(cudaMemsetAsync(s->checksums, 0, sizeof(unsigned long long) * n_frames, ctx->stream));
+    size_t n = (size_t)s->w * s->h;
+    dim3 grid((unsigned)std::min<size_t>((n + 255) / 256, 256), n_frames);
+    cudaEvent_t a, b;
+    prof_begin(ctx, PROF_OTHER, &a, &b);
+    checksum_kernel<<<grid, 256, 0, ctx->stream>>>(s->color, s->depth, n, n, s->checksums);
+    prof_end(ctx, PROF_OTHER, a, b);
+    ctx->launches++;
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaMemcpyAsync(out_host, s->checksums, sizeof(uint64_t) * n_frames, cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(cudaStreamSynchronize(ctx->stream));
+    return HANA_OK;
+}
+extern "C" int hana_sweep_stats(hana_sweep* s, int frame, HanaStats* out) {
+    if (!s || !out) return fail(HANA_E_INVALID, "NULL argument");
+    if (frame < 0 || frame >= s->last_frames) return fail(HANA_E_INVALID, "frame outside the last batch");
+    hana_ctx* ctx = s->ctx;
+    HANA_TRY(use_device(ctx));
+    CU_TRY(cudaMemsetAsync(s->pix_counts, 0, sizeof(uint32_t) * s->last_frames, ctx->stream));
+    size_t n = (size_t)s->w * s->h;
+    dim3 grid((unsigned)std::min<size_t>((n + 255) / 256, 256), s->last_frames);
+    count_written_kernel<<<grid, 256, 0, ctx->stream>>>(s->depth, n, n, s->last_clear_depth, s->pix_counts);
+    ctx->launches++;
+    CU_TRY(cudaGetLastError());
+    uint32_t px = 0;
+    CU_TRY(cudaMemcpyAsync(&px, s->pix_counts + frame, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(cudaStreamSynchronize(ctx->stream));
+    *out = s->last_stats;
+    out->pixels_covered = px;
+    if (frame < (int)s->last_tri_counts[1].size()) out->tris_out = s->last_tri_counts[1][frame];
+    return HANA_OK;
+}
+
+/* ---- host-buffer entry point (what the drop-in graphics shim and the e2e bench call) ---- */
+extern "C" int hana_draw_model_host(hana_ctx* ctx, int width, int height, uint8_t* frame_color_rgba, float* frame_depth,
+                                    const hana_model* model, int shader_id, const HanaUniforms* uniforms,
+                                    const hana_texture* diffuse, const hana_texture* normal, int assume_cleared,
+                                    const uint8_t clear_rgba[4], float clear_depth) {
+    HANA_TRY(check_draw_args(ctx, model, uniforms, shader_id));
+    if (!frame_color_rgba || !frame_depth) return fail(HANA_E_INVALID, "frame buffers are NULL");
+    HANA_TRY(use_device(ctx));
+    if (assume_cleared) {
+        if (!clear_rgba) return fail(HANA_E_INVALID, "clear_rgba is NULL");
+        hana_sweep*& sw = ctx->host_sweep;
+        if (sw && (sw->w != width || sw->h != height)) {
+            hana_sweep_destroy(sw);
+            sw = nullptr;
+        }
+        if (!sw) HANA_TRY(hana_sweep_create(ctx, width, height, 1, &sw));
+        HANA_TRY(hana_sweep_render(sw, model, shader_id, uniforms, 1, diffuse, normal, clear_rgba, clear_depth));
+        return hana_sweep_download(sw, 0, frame_color_rgba, frame_depth);
+    }
+    hana_rb*& fr = ctx->host_frame;
+    hana_rb*& sh = ctx->host_shadow;
+    if (fr && (fr->w != width || fr->h != height)) {
+        hana_rb_destroy(fr);
+        fr = nullptr;
+        hana_rb_destroy(sh);
+        sh = nullptr;
+    }
+    if (!fr) HANA_TRY(hana_rb_create(ctx, width, height, &fr));
+    if (uniforms->enable_shadow && !sh) {
+        HANA_TRY(hana_rb_create(ctx, width, height, &sh));
+        HANA_TRY(hana_rb_clear_color(sh, 0, 0, 0, 1));
+        HANA_TRY(hana_rb_clear_depth(sh, 3.402823466e+38f));
+    }
+    HANA_TRY(hana_rb_upload(fr, frame_color_rgba, frame_depth));
+    HANA_TRY(hana_draw_model(ctx, fr, sh, model, shader_id, uniforms, diffuse, normal));
+    return hana_rb_download(fr, frame_color_rgba, frame_depth);
+}
+
+extern "C" int hana_host_alloc(size_t bytes, void** out) {
+    if (!out) return fail(HANA_E_INVALID, "out is NULL");
+    CU_TRY(cudaMallocHost(out, bytes ? bytes : 1));
+    return HANA_OK;
+}
+extern "C" int hana_host_free(void* p) {
+    if (p) CU_TRY(cudaFreeHost(p));
+    return HANA_OK;
+}
+
+/* ---- stage-level entry points ------------------------------------------------------- */
+extern "C" int hana_stage_vertex(hana_ctx* ctx, const hana_model* model, int shader_id, const HanaUniforms* uniforms,
+                                 float* out_v2f_host) {
+    HANA_TRY(check_draw_args(ctx, model, uniforms, shader_id));
+    if (!out_v2f_host) return fail(HANA_E_INVALID, "out is NULL");
+    HANA_TRY(use_device(ctx));
+    HANA_TRY(upload_uniforms(ctx, uniforms, 1, ctx->u_raw, ctx->u_dev));
+    int n = model->ncorners;
+    if (n == 0) return HANA_OK;
+    float* out = nullptr;
+    CU_TRY(cudaMalloc(&out, (size_t)n * V2F_N * 4));
+    vertex_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(model->posu, model->nrmv, n, shader_id, ctx->u_dev, out);
+    ctx->launches++;
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out_v2f_host, out, (size_t)n * V2F_N * 4, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(out);
+    if (e != cudaSuccess) return fail(HANA_E_CUDA, cudaGetErrorString(e));
+    return HANA_OK;
+}
+
+extern "C" int hana_stage_setup(hana_ctx* ctx, const hana_model* model, int shader_id, const HanaUniforms* uniforms, int width,
+                                int height, int capacity, uint32_t* out_order, float* out_v2f, int* out_count) {
+    HANA_TRY(check_draw_args(ctx, model, uniforms, shader_id));
+    if (!out_order || !out_v2f || !out_count || capacity < 1) return fail(HANA_E_INVALID, "bad output arguments");
+    if (width <= 0 || height <= 0 || width > 65535 || height > 65535) return fail(HANA_E_INVALID, "bad target size");
+    HANA_TRY(use_device(ctx));
+    HANA_TRY(upload_uniforms(ctx, uniforms, 1, ctx->u_raw, ctx->u_dev));
+    float* dbg = nullptr;
+    CU_TRY(cudaMalloc(&dbg, (size_t)capacity * 39 * 4));
+    PassDesc d;
+    d.shader = shader_id;
+    d.mode = MODE_RMW;
+    d.n_frames = 1;
+    d.W = width;
+    d.H = height;
+    d.model = model;
+    d.uniforms = ctx->u_dev;
+    d.dbg_v2f = dbg;
+    d.dbg_cap = (uint32_t)capacity;
+    d.setup_only = true;
+    std::vector<uint32_t> tri_counts;
+    d.tri_counts_out = &tri_counts;
+    uint32_t saved_hint = ctx->tri_cap_hint;
+    ctx->tri_cap_hint = 0;
+    int r = run_pass(ctx, d);
+    ctx->tri_cap_hint = saved_hint;
+    if (r != HANA_OK) {
+        cudaFree(dbg);
+        return r;
+    }
+    uint32_t n = tri_counts.empty() ? 0 : tri_counts[0];
+    std::vector<TriRecord> recs(n);
+    std::vector<float> v2f((size_t)n * 39);
+    cudaError_t e = cudaSuccess;
+    if (n) {
+        e = cudaMemcpy(recs.data(), ctx->sc.tri_rec, sizeof(TriRecord) * n, cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess) e = cudaMemcpy(v2f.data(), dbg, (size_t)n * 39 * 4, cudaMemcpyDeviceToHost);
+    }
+    cudaFree(dbg);
+    if (e != cudaSuccess) return fail(HANA_E_CUDA, cudaGetErrorString(e));
+    std::vector<uint32_t> idx(n);
+    for (uint32_t i = 0; i < n; i++) idx[i] = i;
+    std::sort(idx.begin(), idx.end(), [&](uint32_t a, uint32_t b) { return recs[a].key < recs[b].key; });
+    for (uint32_t i = 0; i < n; i++) {
+        out_order[i] = recs[idx[i]].key;
+        memcpy(out_v2f + (size_t)i * 39, v2f.data() + (size_t)idx[i] * 39, 39 * 4);
+    }
+    *out_count = (int)n;
+    return HANA_OK;
+}

@@ -1,0 +1,658 @@
+/*
+ * hana_kernels.cuh — the sm_100a kernels of the rasterisation path.
+ *
+ *   begin_kernel   HanaUniforms -> DevUniforms (matrix products hoisted), counters zeroed
+ *   setup_kernel   vertex shading + homogeneous clip + cull + triangle setup, warp-scan
+ *                  compaction of the surviving triangles, per-tile reference counts
+ *   scan_kernel    exclusive scan of the tile counts -> list offsets + non-empty tile queue
+ *   fill_kernel    triangle indices into the per-tile lists
+ *   raster_kernel  persistent CTAs, one 16x16 tile at a time: coverage + depth resolve in
+ *                  registers, shading of the winning fragment, tile flush by TMA store;
+ *                  empty tiles are cleared by fire-and-forget TMA stores from a constant tile
+ *   vertex_kernel  stage-level entry point (one thread per corner)
+ *   fill32/checksum/count helpers
+ *
+ * Replaces graphics.cpp:378-407 (graphics_draw_triangle) and everything it
+ * calls. Visibility: the reference writes a fragment iff !(z > stored)
+ * (graphics.cpp:359) while walking primitives in submission order, no shader
+ * discards and nothing blends, so the surviving fragment of a pixel is the one
+ * with the smallest depth and, among equal depths, the largest submission key
+ * (SURVEY.md §0). The rasteriser resolves exactly that pair, which makes the
+ * per-tile lists order-free, and shades only the winner.
+ */
+#ifndef HANA_KERNELS_CUH
+#define HANA_KERNELS_CUH
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include "hana_core.cuh"
+
+namespace hana {
+
+constexpr int TILE = 16;             /* screen tile edge (pixels) */
+constexpr int TILE_PIX = TILE * TILE;
+constexpr int RASTER_THREADS = 256;  /* one thread per tile pixel */
+constexpr int CHUNK = 64;            /* triangles staged in shared memory per round */
+constexpr int TILE_BITS = 20;        /* work item = frame << 20 | tile */
+constexpr uint32_t TILE_MASK = (1u << TILE_BITS) - 1u;
+constexpr int SETUP_THREADS = 128;
+constexpr int SCAN_THREADS = 1024;
+
+enum RasterMode {
+    MODE_CLEAR_FOLD = 0, /* target holds (clear colour, clear depth) before the draw; every tile is written once */
+    MODE_RMW = 1,        /* target has contents that take part in the depth test; only covered pixels change */
+    MODE_SHADOW_R8 = 2   /* ShadowShader into the sweep's internal 1-byte-per-texel maps, cleared to 0 */
+};
+
+/* Device-side bookkeeping of one pass (all frames of a batch). */
+struct PassCounters {
+    uint32_t pool_used;     /* tile-list pool entries reserved by scan_kernel */
+    uint32_t n_work;        /* non-empty (frame,tile) items queued */
+    uint32_t work_cursor;   /* raster queue head */
+    uint32_t clear_cursor;  /* clear queue head (all (frame,tile) slots) */
+    uint32_t tri_needed;    /* max over frames of triangles emitted (capacity check) */
+    uint32_t tiles_touched;
+    uint32_t pad[2];
+};
+
+struct PassParams {
+    /* geometry */
+    const float4* posu;   /* per corner: obj_pos.xyz, uv.x */
+    const float4* nrmv;   /* per corner: obj_normal.xyz, uv.y */
+    int nfaces;
+    int n_frames;
+    int W, H, tiles_x, tiles_y, n_tiles;
+    const DevUniforms* uniforms; /* [n_frames] */
+    /* scratch */
+    TriRecord* tri_rec;   /* [n_frames][tri_cap] */
+    float4* tri_attr;     /* [n_frames][tri_cap][attr_quads] */
+    uint32_t tri_cap;
+    uint32_t* tri_count;  /* [n_frames] */
+    uint32_t* tile_count; /* [n_frames][n_tiles] */
+    uint32_t* tile_offset;
+    uint32_t* tile_cursor;
+    uint32_t* refs;       /* pool */
+    uint32_t pool_cap;
+    uint32_t* work;       /* [n_frames*n_tiles] */
+    PassCounters* counters;
+    float* dbg_v2f;       /* optional: [tri_cap][39] post-clip v2f of frame 0 (stage tests) */
+};
+
+struct RasterParams {
+    PassParams p;
+    /* target */
+    uint32_t* color;      /* RGBA8 as u32, (y*W+x), frame stride below */
+    float* depth;
+    size_t frame_stride;  /* pixels between consecutive frames */
+    uint8_t* shadow_out;  /* MODE_SHADOW_R8: [frame][y*pitch + x] */
+    int shadow_out_pitch;
+    size_t shadow_out_frame_stride; /* bytes */
+    uint32_t clear_color; /* RGBA packed */
+    float clear_depth;
+    int use_tma;
+    /* shading inputs */
+    DevTexture diffuse, normal;
+    DevShadow shadow;            /* frame 0; further frames at + shadow_frame_stride bytes */
+    size_t shadow_frame_stride;
+    uint32_t* primid;            /* optional, frame 0 only: W*H order keys */
+    uint32_t* pixels_covered;    /* optional: [n_frames] */
+};
+
+/* ---- small PTX wrappers: TMA (cp.async.bulk.tensor) + mbarrier ------------ */
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* tm, const void* smem, int x, int y, int z) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(tm),
+                 "r"(smem_u32(smem)), "r"(x), "r"(y), "r"(z)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(phase)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(const CUtensorMap* tm, void* smem, uint64_t* bar, int x, int y, int z) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+            smem_u32(smem)),
+        "l"(tm), "r"(smem_u32(bar)), "r"(x), "r"(y), "r"(z)
+        : "memory");
+}
+
+/* ---- begin: uniforms + counters ------------------------------------------- */
+__global__ void begin_kernel(const HanaUniforms* __restrict__ in, DevUniforms* __restrict__ out, int n_frames) {
+    int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f < n_frames) prepare_uniforms(in[f], out[f]);
+}
+
+/* ---- vertex stage only (hana_stage_vertex) -------------------------------- */
+__global__ void vertex_kernel(const float4* __restrict__ posu, const float4* __restrict__ nrmv, int ncorners, int shader,
+                              const DevUniforms* __restrict__ u, float* __restrict__ out13) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= ncorners) return;
+    float4 p = __ldg(posu + i), n = __ldg(nrmv + i); /* coalesced 128-bit loads over the SoA streams */
+    float a[8] = {p.x, p.y, p.z, n.x, n.y, n.z, p.w, n.w};
+    float v[V2F_N];
+    vertex_shader(shader, *u, a, v);
+    for (int k = 0; k < V2F_N; k++) out13[(size_t)i * V2F_N + k] = v[k];
+}
+
+/* ---- setup ------------------------------------------------------------------ */
+template <int SHADER>
+__device__ __forceinline__ void store_triangle(const PassParams& p, int f, uint32_t slot, const TriRecord& r,
+                                               const float* v0, const float* v1, const float* v2) {
+    constexpr int NA = (SHADER == HANA_SHADER_SHADOW || SHADER == HANA_SHADER_GROUND || SHADER == HANA_SHADER_TOON)
+                           ? 1
+                           : (SHADER == HANA_SHADER_TEXTURE ? 2 : (SHADER == HANA_SHADER_TEXTURE_LIGHT ? 5 : 8));
+    constexpr int NQ = (3 * NA + 3) / 4;
+    float4* dst = reinterpret_cast<float4*>(p.tri_rec + (size_t)f * p.tri_cap + slot);
+    dst[0] = make_float4(r.ax, r.ay, r.s0x, r.s0y);
+    dst[1] = make_float4(r.s1x, r.s1y, r.uz, __uint_as_float(r.bbx));
+    dst[2] = make_float4(__uint_as_float(r.bby), r.d0, r.d1, r.d2);
+    dst[3] = make_float4(r.rw0, r.rw1, r.rw2, __uint_as_float(r.key));
+    float a[NQ * 4];
+#pragma unroll
+    for (int k = 0; k < NA; k++) {
+        const int src = shader_attr_src(SHADER, k);
+        a[3 * k + 0] = v0[src];
+        a[3 * k + 1] = v1[src];
+        a[3 * k + 2] = v2[src];
+    }
+#pragma unroll
+    for (int k = 3 * NA; k < NQ * 4; k++) a[k] = 0.f;
+    float4* ad = p.tri_attr + ((size_t)f * p.tri_cap + slot) * NQ;
+#pragma unroll
+    for (int q = 0; q < NQ; q++) ad[q] = make_float4(a[4 * q], a[4 * q + 1], a[4 * q + 2], a[4 * q + 3]);
+    if (p.dbg_v2f && f == 0) {
+        float* d = p.dbg_v2f + (size_t)slot * 39;
+        for (int k = 0; k < V2F_N; k++) {
+            d[k] = v0[k];
+            d[13 + k] = v1[k];
+            d[26 + k] = v2[k];
+        }
+    }
+}
+
+__device__ __forceinline__ void count_tiles(const PassParams& p, int f, const TriRecord& r) {
+    int tx0 = (int)(r.bbx & 0xFFFFu) >> 4, tx1 = (int)(r.bbx >> 16) >> 4;
+    int ty0 = (int)(r.bby & 0xFFFFu) >> 4, ty1 = (int)(r.bby >> 16) >> 4;
+    uint32_t* tc = p.tile_count + (size_t)f * p.n_tiles;
+    for (int ty = ty0; ty <= ty1; ty++)
+        for (int tx = tx0; tx <= tx1; tx++) atomicAdd(tc + ty * p.tiles_x + tx, 1u);
+}
+
+/* Rare path: the face is not trivially accepted. Sutherland-Hodgman in local
+ * memory, then the fan (0, j+1, j+2) of graphics.cpp:394-405. */
+template <int SHADER>
+__device__ __noinline__ void setup_clipped(const PassParams& p, int f, int face, const float* v39) {
+    float poly[10 * V2F_N];
+    for (int i = 0; i < 3 * V2F_N; i++) poly[i] = v39[i];
+    int n = clip_polygon(poly);
+    for (int j = 0; j + 2 < n; j++) {
+        const float* a = poly;
+        const float* b = poly + V2F_N * (j + 1);
+        const float* c = poly + V2F_N * (j + 2);
+        TriRecord r;
+        if (!triangle_setup(a, b, c, p.W, p.H, (uint32_t)face * 8u + (uint32_t)j, r)) continue;
+        uint32_t slot = atomicAdd(p.tri_count + f, 1u);
+        if (slot < p.tri_cap) {
+            store_triangle<SHADER>(p, f, slot, r, a, b, c);
+            count_tiles(p, f, r);
+        }
+    }
+}
+
+template <int SHADER>
+__global__ void __launch_bounds__(SETUP_THREADS) setup_kernel(PassParams p) {
+    const int f = blockIdx.y;
+    const int face = blockIdx.x * SETUP_THREADS + threadIdx.x;
+    const unsigned lane = threadIdx.x & 31u;
+    const DevUniforms& u = p.uniforms[f];
+    bool emit = false;
+    TriRecord r;
+    float v[3 * V2F_N];
+    if (face < p.nfaces) {
+#pragma unroll
+        for (int j = 0; j < 3; j++) { /* graphics.cpp:381-387 */
+            float4 pu = __ldg(p.posu + (size_t)face * 3 + j);
+            float4 nv = __ldg(p.nrmv + (size_t)face * 3 + j);
+            float a[8] = {pu.x, pu.y, pu.z, nv.x, nv.y, nv.z, pu.w, nv.w};
+            vertex_shader(SHADER, u, a, v + V2F_N * j);
+        }
+        if (clip_trivial_accept(v)) {
+            emit = triangle_setup(v, v + V2F_N, v + 2 * V2F_N, p.W, p.H, (uint32_t)face * 8u, r);
+        } else {
+            setup_clipped<SHADER>(p, f, face, v);
+        }
+    }
+    /* warp-shuffle prefix sum over the emit flags -> one atomic per warp */
+    unsigned ballot = __ballot_sync(0xFFFFFFFFu, emit);
+    if (ballot) {
+        int incl = emit ? 1 : 0;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            int t = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+            if ((int)lane >= d) incl += t;
+        }
+        int total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(p.tri_count + f, (uint32_t)total);
+        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+        if (emit) {
+            uint32_t slot = base + (uint32_t)(incl - 1);
+            if (slot < p.tri_cap) {
+                store_triangle<SHADER>(p, f, slot, r, v, v + V2F_N, v + 2 * V2F_N);
+                count_tiles(p, f, r);
+            }
+        }
+    }
+}
+
+/* ---- scan: per frame, tile counts -> offsets into the pool + work queue ---- */
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t val, uint32_t* total, uint32_t* warp_sums /* [32] */) {
+    const unsigned lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
+    uint32_t incl = val;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+        if ((int)lane >= d) incl += t;
+    }
+    if (lane == 31) warp_sums[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+        uint32_t w = (lane < (blockDim.x >> 5)) ? warp_sums[lane] : 0u;
+        uint32_t wi = w;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            uint32_t t = __shfl_up_sync(0xFFFFFFFFu, wi, d);
+            if ((int)lane >= d) wi += t;
+        }
+        warp_sums[lane] = wi - w; /* exclusive */
+        if (lane == 31) *total = wi;
+    }
+    __syncthreads();
+    uint32_t r = warp_sums[wid] + incl - val;
+    __syncthreads();
+    return r;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) scan_kernel(PassParams p) {
+    __shared__ uint32_t warp_sums[32];
+    __shared__ uint32_t s_total_refs, s_total_ne, s_base_refs, s_base_work;
+    const int f = blockIdx.x;
+    const int per = (p.n_tiles + SCAN_THREADS - 1) / SCAN_THREADS;
+    const int t0 = threadIdx.x * per;
+    const int t1 = min(t0 + per, p.n_tiles);
+    const uint32_t* tc = p.tile_count + (size_t)f * p.n_tiles;
+    uint32_t refs = 0, ne = 0;
+    for (int t = t0; t < t1; t++) {
+        uint32_t c = tc[t];
+        refs += c;
+        ne += (c != 0u);
+    }
+    uint32_t ex_refs = block_exclusive_scan(refs, &s_total_refs, warp_sums);
+    uint32_t ex_ne = block_exclusive_scan(ne, &s_total_ne, warp_sums);
+    if (threadIdx.x == 0) {
+        s_base_refs = atomicAdd(&p.counters->pool_used, s_total_refs);
+        s_base_work = atomicAdd(&p.counters->n_work, s_total_ne);
+        atomicAdd(&p.counters->tiles_touched, s_total_ne);
+        atomicMax(&p.counters->tri_needed, p.tri_count[f]);
+    }
+    __syncthreads();
+    uint32_t off = s_base_refs + ex_refs;
+    uint32_t wi = s_base_work + ex_ne;
+    uint32_t* to = p.tile_offset + (size_t)f * p.n_tiles;
+    for (int t = t0; t < t1; t++) {
+        uint32_t c = tc[t];
+        to[t] = off;
+        off += c;
+        if (c) p.work[wi++] = ((uint32_t)f << TILE_BITS) | (uint32_t)t;
+    }
+}
+
+/* ---- fill: triangle indices into the tile lists ----------------------------- */
+__global__ void __launch_bounds__(256) fill_kernel(PassParams p) {
+    const int f = blockIdx.y;
+    const uint32_t i = blockIdx.x * 256u + threadIdx.x;
+    uint32_t n = p.tri_count[f];
+    if (n > p.tri_cap) n = p.tri_cap;
+    if (i >= n) return;
+    if (p.counters->pool_used > p.pool_cap) return; /* host re-runs the pass with a larger pool */
+    const float4* rec = reinterpret_cast<const float4*>(p.tri_rec + (size_t)f * p.tri_cap + i);
+    uint32_t bbx = __float_as_uint(__ldg(rec + 1).w);
+    uint32_t bby = __float_as_uint(__ldg(rec + 2).x);
+    int tx0 = (int)(bbx & 0xFFFFu) >> 4, tx1 = (int)(bbx >> 16) >> 4;
+    int ty0 = (int)(bby & 0xFFFFu) >> 4, ty1 = (int)(bby >> 16) >> 4;
+    uint32_t* cur = p.tile_cursor + (size_t)f * p.n_tiles;
+    const uint32_t* to = p.tile_offset + (size_t)f * p.n_tiles;
+    for (int ty = ty0; ty <= ty1; ty++)
+        for (int tx = tx0; tx <= tx1; tx++) {
+            int t = ty * p.tiles_x + tx;
+            uint32_t s = atomicAdd(cur + t, 1u);
+            p.refs[to[t] + s] = i;
+        }
+}
+
+/* ---- raster ------------------------------------------------------------------ */
+struct alignas(128) RasterSmem {
+    uint32_t out_color[TILE_PIX]; /* 1 KB, TMA box 16x16 u32 */
+    float out_depth[TILE_PIX];
+    uint32_t clr_color[TILE_PIX]; /* constant clear tiles, TMA store source for empty tiles */
+    float clr_depth[TILE_PIX];
+    float4 tri[CHUNK * 4];        /* staged TriRecords */
+    uint32_t tri_idx[CHUNK];
+    alignas(128) uint8_t out_r8[TILE_PIX]; /* MODE_SHADOW_R8 tile, box 16x16 u8 */
+    alignas(128) uint8_t clr_r8[TILE_PIX];
+    alignas(8) uint64_t bar;
+    uint32_t item;
+    uint32_t clear_base;
+};
+
+/* One warp claims 32 consecutive (frame,tile) slots and clears those no triangle touches:
+ * by TMA, two fire-and-forget bulk stores per lane from the constant tiles. Returns true
+ * when the queue is exhausted. */
+template <int MODE>
+__device__ __forceinline__ bool clear_slots(const RasterParams& q, RasterSmem& sm, const CUtensorMap& tm_color,
+                                            const CUtensorMap& tm_depth, const CUtensorMap& tm_r8, uint32_t n_slots) {
+    const PassParams& p = q.p;
+    const unsigned lane = threadIdx.x & 31u;
+    uint32_t base = 0;
+    if (lane == 0) base = atomicAdd(&p.counters->clear_cursor, 32u);
+    base = __shfl_sync(0xFFFFFFFFu, base, 0);
+    if (base >= n_slots) return true;
+    const uint32_t s = base + lane;
+    if (s < n_slots && p.tile_count[s] == 0u) {
+        const int f = (int)(s / (uint32_t)p.n_tiles), t = (int)(s % (uint32_t)p.n_tiles);
+        const int tx = t % p.tiles_x, ty = t / p.tiles_x;
+        if (q.use_tma) {
+            if (MODE == MODE_SHADOW_R8) {
+                tma_store_3d(&tm_r8, sm.clr_r8, tx * TILE, ty * TILE, f);
+            } else {
+                tma_store_3d(&tm_color, sm.clr_color, tx * TILE, ty * TILE, f);
+                tma_store_3d(&tm_depth, sm.clr_depth, tx * TILE, ty * TILE, f);
+            }
+            tma_commit();
+        } else {
+            for (int yy = 0; yy < TILE; yy++) {
+                const int py = ty * TILE + yy;
+                if (py >= p.H) break;
+                for (int xx = 0; xx < TILE; xx++) {
+                    const int px = tx * TILE + xx;
+                    if (px >= p.W) break;
+                    if (MODE == MODE_SHADOW_R8) {
+                        q.shadow_out[(size_t)f * q.shadow_out_frame_stride + (size_t)py * q.shadow_out_pitch + px] = 0;
+                    } else {
+                        const size_t o = (size_t)f * q.frame_stride + (size_t)py * p.W + px;
+                        q.color[o] = q.clear_color;
+                        q.depth[o] = q.clear_depth;
+                    }
+                }
+            }
+        }
+    }
+    return false;
+}
+
+template <int SHADER, int MODE>
+__global__ void __launch_bounds__(RASTER_THREADS)
+    raster_kernel(RasterParams q, const __grid_constant__ CUtensorMap tm_color, const __grid_constant__ CUtensorMap tm_depth,
+                  const __grid_constant__ CUtensorMap tm_r8) {
+    constexpr int NA = (SHADER == HANA_SHADER_SHADOW || SHADER == HANA_SHADER_GROUND || SHADER == HANA_SHADER_TOON)
+                           ? 1
+                           : (SHADER == HANA_SHADER_TEXTURE ? 2 : (SHADER == HANA_SHADER_TEXTURE_LIGHT ? 5 : 8));
+    constexpr int NQ = (3 * NA + 3) / 4;
+    __shared__ RasterSmem sm;
+    const PassParams& p = q.p;
+    const int tid = threadIdx.x;
+    const unsigned lane = tid & 31u, wid = tid >> 5;
+    /* warp w owns an 8x4 pixel block of the tile: 2 blocks across, 4 down */
+    const int lx = (int)(wid & 1u) * 8 + (int)(lane & 7u);
+    const int ly = (int)(wid >> 1) * 4 + (int)(lane >> 3);
+    const int wbx = (int)(wid & 1u) * 8, wby = (int)(wid >> 1) * 4;
+    const bool tma = q.use_tma != 0;
+
+    if (p.counters->pool_used > p.pool_cap) return; /* lists are incomplete: host re-runs with a larger pool */
+
+    /* constant clear tiles */
+    if (MODE != MODE_RMW) {
+        sm.clr_color[tid] = q.clear_color;
+        sm.clr_depth[tid] = q.clear_depth;
+        sm.clr_r8[tid] = 0;
+    }
+    if (tid == 0) {
+        sm.item = atomicAdd(&p.counters->work_cursor, 1u);
+        if (MODE == MODE_RMW) {
+            mbar_init(&sm.bar, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+    }
+    fence_async_smem();
+    __syncthreads();
+
+    const uint32_t n_work = p.counters->n_work;
+    const uint32_t n_slots = (uint32_t)p.n_frames * (uint32_t)p.n_tiles;
+    bool clear_done = (MODE == MODE_RMW); /* per warp */
+    uint32_t load_phase = 0;
+    uint32_t covered_acc = 0;
+
+    while (true) {
+        const uint32_t it = sm.item;
+        __syncthreads();
+        if (it >= n_work) break; /* uniform: every thread read the same item */
+        if (tid == 0) sm.item = atomicAdd(&p.counters->work_cursor, 1u); /* prefetch; published by the syncs below */
+
+        /* clear duty while raster work remains: warp 1 claims 32 (frame,tile) slots per tile it helps rasterise */
+        if (MODE != MODE_RMW && wid == 1 && !clear_done) clear_done = clear_slots<MODE>(q, sm, tm_color, tm_depth, tm_r8, n_slots);
+
+        /* -- one non-empty tile -- */
+        const int f = (int)(it >> TILE_BITS);
+        const int t = (int)(it & TILE_MASK);
+        const int tx = t % p.tiles_x, ty = t / p.tiles_x;
+        const int px = tx * TILE + lx, py = ty * TILE + ly;
+        const bool in_frame = px < p.W && py < p.H;
+        const uint32_t cnt = p.tile_count[(size_t)f * p.n_tiles + t];
+        const uint32_t off = p.tile_offset[(size_t)f * p.n_tiles + t];
+        const TriRecord* recs = p.tri_rec + (size_t)f * p.tri_cap;
+
+        float bz = q.clear_depth;
+        uint32_t bcol = q.clear_color;
+        if (MODE == MODE_RMW) {
+            if (tma) {
+                if (tid == 0) {
+                    tma_wait_read0(); /* the previous tile's stores have read out_color/out_depth */
+                    mbar_expect_tx(&sm.bar, 2u * TILE_PIX * 4u);
+                    tma_load_3d(&tm_color, sm.out_color, &sm.bar, tx * TILE, ty * TILE, f);
+                    tma_load_3d(&tm_depth, sm.out_depth, &sm.bar, tx * TILE, ty * TILE, f);
+                }
+                mbar_wait(&sm.bar, load_phase);
+                load_phase ^= 1u;
+                bz = sm.out_depth[ly * TILE + lx];
+                bcol = sm.out_color[ly * TILE + lx];
+            } else if (in_frame) {
+                size_t o = (size_t)f * q.frame_stride + (size_t)py * p.W + px;
+                bz = q.depth[o];
+                bcol = q.color[o];
+            }
+        }
+        int bkey = -1;
+        uint32_t bidx = 0;
+        float bw0 = 0.f, bw1 = 0.f, bw2 = 0.f;
+        const float fpx = (float)px, fpy = (float)py;
+
+        for (uint32_t c0 = 0; c0 < cnt; c0 += CHUNK) {
+            const int n = (int)min((uint32_t)CHUNK, cnt - c0);
+            __syncthreads(); /* previous chunk fully consumed */
+            if (tid < n * 4) {
+                uint32_t ti = p.refs[off + c0 + (tid >> 2)];
+                sm.tri[tid] = __ldg(reinterpret_cast<const float4*>(recs + ti) + (tid & 3));
+                if ((tid & 3) == 0) sm.tri_idx[tid >> 2] = ti;
+            }
+            __syncthreads();
+            for (int j = 0; j < n; j++) {
+                const float4 r1 = sm.tri[j * 4 + 1];
+                const float4 r2 = sm.tri[j * 4 + 2];
+                const uint32_t bbx = __float_as_uint(r1.w), bby = __float_as_uint(r2.x);
+                const int x0 = (int)(bbx & 0xFFFFu), x1 = (int)(bbx >> 16);
+                const int y0 = (int)(bby & 0xFFFFu), y1 = (int)(bby >> 16);
+                /* warp-uniform reject of the 8x4 block against the triangle's pixel range */
+                const int bx = tx * TILE + wbx, by = ty * TILE + wby;
+                if (x1 < bx || x0 > bx + 7 || y1 < by || y0 > by + 3) continue;
+                const float4 r0 = sm.tri[j * 4 + 0];
+                float ux, uy;
+                bool cov = coverage_test(r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, fpx, fpy, ux, uy);
+                cov = cov && px >= x0 && px <= x1 && py >= y0 && py <= y1;
+                if (cov) {
+                    float w0, w1, w2;
+                    barycentric_weights(ux, uy, r1.z, w0, w1, w2);
+                    float z = interpolate_depth(r2.y, r2.z, r2.w, w0, w1, w2);
+                    int key = (int)__float_as_uint(sm.tri[j * 4 + 3].w);
+                    bool win = (bkey < 0) ? !(z > bz) : (z < bz || (z == bz && key > bkey));
+                    if (win) {
+                        bz = z;
+                        bkey = key;
+                        bidx = sm.tri_idx[j];
+                        bw0 = w0;
+                        bw1 = w1;
+                        bw2 = w2;
+                    }
+                }
+            }
+        }
+
+        /* -- shade the winner (graphics.cpp:362-373) -- */
+        if (bkey >= 0) {
+            const float4 r3 = __ldg(reinterpret_cast<const float4*>(recs + bidx) + 3);
+            VaryingWeights vw = varying_weights(bw0, bw1, bw2, r3.x, r3.y, r3.z);
+            const float4* ap = p.tri_attr + ((size_t)f * p.tri_cap + bidx) * NQ;
+            float a[NQ * 4];
+#pragma unroll
+            for (int k = 0; k < NQ; k++) {
+                float4 v = __ldg(ap + k);
+                a[4 * k] = v.x;
+                a[4 * k + 1] = v.y;
+                a[4 * k + 2] = v.z;
+                a[4 * k + 3] = v.w;
+            }
+            float attr[NA];
+#pragma unroll
+            for (int k = 0; k < NA; k++) attr[k] = interp(vw, a[3 * k], a[3 * k + 1], a[3 * k + 2]);
+            DevShadow sh = q.shadow;
+            if (sh.base) sh.base += (size_t)f * q.shadow_frame_stride;
+            float rgb[3];
+            fragment_shader<SHADER>(p.uniforms[f], attr, q.diffuse, q.normal, sh, rgb);
+            bcol = (bcol & 0xFF000000u) | colour_bytes(rgb); /* alpha is never written: renderbuffer.cpp:38-44 */
+            if (q.primid && f == 0) q.primid[(size_t)py * p.W + px] = (uint32_t)bkey;
+        }
+        if (q.pixels_covered) covered_acc += __popc(__ballot_sync(0xFFFFFFFFu, bkey >= 0));
+
+        /* -- flush -- */
+        if (tma) {
+            if (MODE != MODE_RMW) {
+                if (tid == 0) tma_wait_read0(); /* previous tile's store has drained the staging tile */
+                __syncthreads();
+            }
+            if (MODE == MODE_SHADOW_R8) {
+                sm.out_r8[ly * TILE + lx] = (uint8_t)(bkey >= 0 ? (bcol & 255u) : 0u);
+            } else {
+                sm.out_color[ly * TILE + lx] = bcol;
+                sm.out_depth[ly * TILE + lx] = bz;
+            }
+            fence_async_smem();
+            __syncthreads();
+            if (tid == 0) {
+                if (MODE == MODE_SHADOW_R8) {
+                    tma_store_3d(&tm_r8, sm.out_r8, tx * TILE, ty * TILE, f);
+                } else {
+                    tma_store_3d(&tm_color, sm.out_color, tx * TILE, ty * TILE, f);
+                    tma_store_3d(&tm_depth, sm.out_depth, tx * TILE, ty * TILE, f);
+                }
+                tma_commit();
+            }
+        } else if (in_frame) {
+            if (MODE == MODE_SHADOW_R8) {
+                q.shadow_out[(size_t)f * q.shadow_out_frame_stride + (size_t)py * q.shadow_out_pitch + px] =
+                    (uint8_t)(bkey >= 0 ? (bcol & 255u) : 0u);
+            } else if (MODE == MODE_CLEAR_FOLD || bkey >= 0) {
+                size_t o = (size_t)f * q.frame_stride + (size_t)py * p.W + px;
+                q.color[o] = bcol;
+                q.depth[o] = bz;
+            }
+        }
+        if (q.pixels_covered && lane == 0 && covered_acc) {
+            atomicAdd(q.pixels_covered + f, covered_acc);
+            covered_acc = 0;
+        }
+    }
+    /* raster queue drained: every warp helps with what is left of the clear queue */
+    if (MODE != MODE_RMW)
+        while (!clear_done) clear_done = clear_slots<MODE>(q, sm, tm_color, tm_depth, tm_r8, n_slots);
+    /* shared memory must outlive the bulk stores that read it */
+    tma_wait_read0();
+}
+
+/* ---- helpers ---------------------------------------------------------------- */
+__global__ void fill32_kernel(uint32_t* __restrict__ dst, uint32_t value, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    size_t n4 = n / 4;
+    uint4 v = make_uint4(value, value, value, value);
+    uint4* d4 = reinterpret_cast<uint4*>(dst);
+    for (size_t k = i; k < n4; k += stride) d4[k] = v;
+    for (size_t k = n4 * 4 + i; k < n; k += stride) dst[k] = value;
+}
+
+/* Order-independent 64-bit frame checksum: sum over pixels of mix(index, RGB, depth bits).
+ * tests/ and the multi-GPU sharding check recompute it with numpy. */
+__device__ __forceinline__ uint64_t mix64(uint64_t x) {
+    x ^= x >> 33;
+    x *= 0xff51afd7ed558ccdULL;
+    x ^= x >> 33;
+    x *= 0xc4ceb9fe1a85ec53ULL;
+    x ^= x >> 33;
+    return x;
+}
+__global__ void checksum_kernel(const uint32_t* __restrict__ color, const float* __restrict__ depth, size_t frame_stride,
+                                size_t npix, unsigned long long* __restrict__ out) {
+    const int f = blockIdx.y;
+    const uint32_t* c = color + (size_t)f * frame_stride;
+    const float* d = depth + (size_t)f * frame_stride;
+    uint64_t acc = 0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += (size_t)gridDim.x * blockDim.x) {
+        uint64_t v = ((uint64_t)(c[i] & 0x00FFFFFFu) << 32) | (uint64_t)__float_as_uint(d[i]);
+        acc += mix64(v ^ mix64((uint64_t)i + 0x9E3779B97F4A7C15ULL));
+    }
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xFFFFFFFFu, acc, o);
+    if ((threadIdx.x & 31) == 0 && acc) atomicAdd(out + f, (unsigned long long)acc);
+}
+
+/* pixels whose depth differs from the clear depth (sweep statistics) */
+__global__ void count_written_kernel(const float* __restrict__ depth, size_t frame_stride, size_t npix, float clear_depth,
+                                     uint32_t* __restrict__ out) {
+    const int f = blockIdx.y;
+    const float* d = depth + (size_t)f * frame_stride;
+    uint32_t acc = 0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += (size_t)gridDim.x * blockDim.x)
+        acc += (__float_as_uint(d[i]) != __float_as_uint(clear_depth));
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xFFFFFFFFu, acc, o);
+    if ((threadIdx.x & 31) == 0 && acc) atomicAdd(out + f, acc);
+}
+
+}  // namespace hana
+#endif /* HANA_KERNELS_CUH */

@@ -32,6 +32,12 @@
 extern "C" {
 #endif
 
+#if defined(__GNUC__)
+#define HANA_API __attribute__((visibility("default")))
+#else
+#define HANA_API
+#endif
+
 #define HANA_OK 0
 #define HANA_E_INVALID (-1)   /* bad argument */
 #define HANA_E_CUDA (-2)      /* CUDA runtime/driver error (message has the cudaError string) */
@@ -90,51 +96,75 @@ typedef struct hana_texture hana_texture;
 typedef struct hana_rb hana_rb;
 typedef struct hana_sweep hana_sweep;
 
-const char* hana_last_error(void);
-int hana_version(void);
-int hana_device_count(void);
+HANA_API const char* hana_last_error(void);
+HANA_API int hana_version(void);
+HANA_API int hana_device_count(void);
 
 /* --- context ------------------------------------------------------------ */
-int hana_ctx_create(int device, hana_ctx** out);
-int hana_ctx_destroy(hana_ctx* ctx);
+HANA_API int hana_ctx_create(int device, hana_ctx** out);
+HANA_API int hana_ctx_destroy(hana_ctx* ctx);
 /* Launch on an existing cudaStream_t (e.g. torch's current stream) instead of
  * the context's own non-blocking stream; pass NULL to go back. */
-int hana_ctx_set_stream(hana_ctx* ctx, void* cuda_stream);
-int hana_sync(hana_ctx* ctx);
+HANA_API int hana_ctx_set_stream(hana_ctx* ctx, void* cuda_stream);
+HANA_API int hana_sync(hana_ctx* ctx);
 /* Number of kernels this context has launched so far (bench "gpu_launches"). */
-int hana_ctx_launch_count(hana_ctx* ctx, uint64_t* out);
+HANA_API int hana_ctx_launch_count(hana_ctx* ctx, uint64_t* out);
+/* Tile flush / clear through TMA bulk tensor stores (default when the driver exposes
+ * cuTensorMapEncodeTiled and the target's row stride is a multiple of 16 bytes) or
+ * plain global stores. HANA_NO_TMA=1 in the environment selects the latter at creation. */
+HANA_API int hana_ctx_uses_tma(hana_ctx* ctx);
+HANA_API int hana_ctx_set_tma(hana_ctx* ctx, int enable);
+HANA_API int hana_ctx_sm_count(hana_ctx* ctx);
+
+/* --- measurement ------------------------------------------------------------ */
+/* CUDA-event timing on the context's stream. hana_timer_stop synchronises. */
+HANA_API int hana_timer_start(hana_ctx* ctx);
+HANA_API int hana_timer_stop(hana_ctx* ctx, float* ms);
+/* Per-kernel-class device time: when enabled, every launch is bracketed by a
+ * pair of events on the launching stream; _get sums them (after they completed). */
+#define HANA_PROF_BEGIN 0
+#define HANA_PROF_SETUP 1
+#define HANA_PROF_SCAN 2
+#define HANA_PROF_FILL 3
+#define HANA_PROF_RASTER_SHADOW 4
+#define HANA_PROF_RASTER_MAIN 5
+#define HANA_PROF_OTHER 6
+#define HANA_PROF_KINDS 7
+HANA_API int hana_ctx_profile(hana_ctx* ctx, int enable);
+HANA_API int hana_ctx_profile_reset(hana_ctx* ctx);
+HANA_API int hana_ctx_profile_get(hana_ctx* ctx, int kind, double* total_ms, uint64_t* launches);
 
 /* --- inputs --------------------------------------------------------------- */
 /* a2v: ncorners records of shader_struct_a2v (IShader.h:35-39): 8 floats
  * {obj_pos.xyz, obj_normal.xyz, uv.xy}, 3 consecutive corners per face in the
  * order graphics.cpp:380-386 visits them. ncorners must be a multiple of 3. */
-int hana_model_upload(hana_ctx* ctx, const float* a2v, int ncorners, hana_model** out);
-int hana_model_destroy(hana_model* m);
-int hana_model_ncorners(const hana_model* m);
+HANA_API int hana_model_upload(hana_ctx* ctx, const float* a2v, int ncorners, hana_model** out);
+HANA_API int hana_model_destroy(hana_model* m);
+HANA_API int hana_model_ncorners(const hana_model* m);
 
 /* data: TGAImage::buffer() layout (tgaimage.cpp:248-253): w*h texels of
  * bytespp (1, 3 or 4) bytes in B,G,R,A order, row y at data + y*w*bytespp. */
-int hana_texture_upload(hana_ctx* ctx, const uint8_t* data, int w, int h, int bytespp,
+HANA_API int hana_texture_upload(hana_ctx* ctx, const uint8_t* data, int w, int h, int bytespp,
                         hana_texture** out);
-int hana_texture_destroy(hana_texture* t);
+HANA_API int hana_texture_destroy(hana_texture* t);
 
 /* --- render target (RenderBuffer, renderbuffer.h:5-22) -------------------- */
 /* Device-resident colour (RGBA8, index (y*w+x)*4, y up) + depth (f32, y*w+x).
  * A fresh buffer holds what the reference ctor leaves: colour (0,0,0,255),
  * depth 1.0 (renderbuffer.cpp:6-7,16-17). */
-int hana_rb_create(hana_ctx* ctx, int width, int height, hana_rb** out);
-int hana_rb_destroy(hana_rb* rb);
-int hana_rb_size(const hana_rb* rb, int* width, int* height);
+HANA_API int hana_rb_create(hana_ctx* ctx, int width, int height, hana_rb** out);
+HANA_API int hana_rb_destroy(hana_rb* rb);
+HANA_API int hana_rb_size(const hana_rb* rb, int* width, int* height);
 /* renderbuffer_clear_color writes all four bytes (renderbuffer.cpp:59-68);
  * the bytes are given directly because Color{...,a=255}*255 is out of range
  * for unsigned char in the reference. */
-int hana_rb_clear_color(hana_rb* rb, uint8_t r, uint8_t g, uint8_t b, uint8_t a);
-int hana_rb_clear_depth(hana_rb* rb, float depth);
+HANA_API int hana_rb_clear_color(hana_rb* rb, uint8_t r, uint8_t g, uint8_t b, uint8_t a);
+HANA_API int hana_rb_clear_depth(hana_rb* rb, float depth);
 /* Either pointer may be NULL to skip that plane. Host pointers; synchronous. */
-int hana_rb_upload(hana_rb* rb, const uint8_t* color_rgba, const float* depth);
-int hana_rb_download(hana_rb* rb, uint8_t* color_rgba, float* depth);
+HANA_API int hana_rb_upload(hana_rb* rb, const uint8_t* color_rgba, const float* depth);
+HANA_API int hana_rb_download(hana_rb* rb, uint8_t* color_rgba, float* depth);
 /* Raw device pointers (for zero-copy consumers such as the bench harness). */
-int hana_rb_device_ptrs(hana_rb* rb, void** color_dev, void** depth_dev);
+HANA_API int hana_rb_device_ptrs(hana_rb* rb, void** color_dev, void** depth_dev);
 
 /* --- the draw entry points -------------------------------------------------- */
 /* One pass over all faces of `model` with device shader `shader_id`:
@@ -145,14 +175,14 @@ int hana_rb_device_ptrs(hana_rb* rb, void** color_dev, void** depth_dev);
  * alpha is never written). diffuse/normal may be NULL (fetches return 0 as
  * TGAImage::get does without data); shadow_map may be NULL
  * (IShader.h:109 -> lit). Asynchronous on the context's stream. */
-int hana_draw(hana_ctx* ctx, hana_rb* rb, const hana_model* model, int shader_id,
+HANA_API int hana_draw(hana_ctx* ctx, hana_rb* rb, const hana_model* model, int shader_id,
               const HanaUniforms* uniforms, const hana_texture* diffuse,
               const hana_texture* normal, const hana_rb* shadow_map);
 
 /* DrawModel::draw (scene.h:53-99): if u->enable_shadow, ShadowShader pass
  * into `shadow_map`, then `shader_id` pass into `frame` reading it, then
  * shadow_map cleared to (0,0,0,[255*255 -> 1]) / FLT_MAX (scene.h:94-98). */
-int hana_draw_model(hana_ctx* ctx, hana_rb* frame, hana_rb* shadow_map, const hana_model* model,
+HANA_API int hana_draw_model(hana_ctx* ctx, hana_rb* frame, hana_rb* shadow_map, const hana_model* model,
                     int shader_id, const HanaUniforms* uniforms, const hana_texture* diffuse,
                     const hana_texture* normal);
 
@@ -163,13 +193,13 @@ int hana_draw_model(hana_ctx* ctx, hana_rb* frame, hana_rb* shadow_map, const ha
  * call the drop-in graphics_draw_triangle shim and the bench's e2e leg use.
  * If assume_cleared != 0 the frame is taken to hold (clear_rgba, clear_depth)
  * everywhere and the upload is skipped. */
-int hana_draw_model_host(hana_ctx* ctx, int width, int height, uint8_t* frame_color_rgba,
+HANA_API int hana_draw_model_host(hana_ctx* ctx, int width, int height, uint8_t* frame_color_rgba,
                          float* frame_depth, const hana_model* model, int shader_id,
                          const HanaUniforms* uniforms, const hana_texture* diffuse,
                          const hana_texture* normal, int assume_cleared,
                          const uint8_t clear_rgba[4], float clear_depth);
 
-int hana_last_stats(hana_ctx* ctx, HanaStats* out); /* synchronises */
+HANA_API int hana_last_stats(hana_ctx* ctx, HanaStats* out); /* synchronises */
 
 /* --- batched frame sweep (BASELINE.json configs[2]) ------ */
 /* Renders n_frames independent frames of one model per submission: for each
@@ -177,51 +207,54 @@ int hana_last_stats(hana_ctx* ctx, HanaStats* out); /* synchronises */
  * i.e. main.cpp:152-153 + DrawModel::draw — with the frame index as a grid
  * dimension, so launch latency is paid once per batch. Frames land in a
  * device ring of `n_frames` colour+depth targets. */
-int hana_sweep_create(hana_ctx* ctx, int width, int height, int max_frames, hana_sweep** out);
-int hana_sweep_destroy(hana_sweep* s);
+HANA_API int hana_sweep_create(hana_ctx* ctx, int width, int height, int max_frames, hana_sweep** out);
+HANA_API int hana_sweep_destroy(hana_sweep* s);
 /* uniforms: host array of n_frames HanaUniforms (copied H2D inside). */
-int hana_sweep_render(hana_sweep* s, const hana_model* model, int shader_id,
+HANA_API int hana_sweep_render(hana_sweep* s, const hana_model* model, int shader_id,
                       const HanaUniforms* uniforms, int n_frames, const hana_texture* diffuse,
                       const hana_texture* normal, const uint8_t clear_rgba[4], float clear_depth);
+/* Device buffer (max_frames * sizeof(HanaUniforms)) a caller may fill itself and hand to
+ * hana_sweep_render_dev to keep the whole submission free of host->device copies. */
+HANA_API int hana_sweep_uniforms_dev(hana_sweep* s, void** out);
 /* Same, uniforms already resident on the device (n_frames * sizeof(HanaUniforms)). */
-int hana_sweep_render_dev(hana_sweep* s, const hana_model* model, int shader_id,
+HANA_API int hana_sweep_render_dev(hana_sweep* s, const hana_model* model, int shader_id,
                           const void* uniforms_dev, int n_frames, const hana_texture* diffuse,
                           const hana_texture* normal, const uint8_t clear_rgba[4], float clear_depth);
 /* Copy frame `i` of the last batch to host (either may be NULL). Synchronous. */
-int hana_sweep_download(hana_sweep* s, int frame, uint8_t* color_rgba, float* depth);
+HANA_API int hana_sweep_download(hana_sweep* s, int frame, uint8_t* color_rgba, float* depth);
 /* Async copy of frames [first, first+count) into caller-provided PINNED host
  * memory (count*W*H*4 bytes each plane; depth may be NULL); ordered on the
  * context's stream. */
-int hana_sweep_download_async(hana_sweep* s, int first, int count, uint8_t* color_rgba_pinned,
+HANA_API int hana_sweep_download_async(hana_sweep* s, int first, int count, uint8_t* color_rgba_pinned,
                               float* depth_pinned);
-int hana_sweep_device_ptrs(hana_sweep* s, void** color_dev, void** depth_dev,
+HANA_API int hana_sweep_device_ptrs(hana_sweep* s, void** color_dev, void** depth_dev,
                            size_t* frame_stride_pixels);
 /* Per-frame 64-bit checksum (FNV-style over RGB bytes and depth bits) of the
  * last batch, computed on the device; used by the multi-GPU sharding tests. */
-int hana_sweep_checksums(hana_sweep* s, int n_frames, uint64_t* out_host);
-int hana_sweep_stats(hana_sweep* s, int frame, HanaStats* out); /* synchronises */
+HANA_API int hana_sweep_checksums(hana_sweep* s, int n_frames, uint64_t* out_host);
+HANA_API int hana_sweep_stats(hana_sweep* s, int frame, HanaStats* out); /* synchronises */
 
 /* Pinned host memory helpers for the e2e path. */
-int hana_host_alloc(size_t bytes, void** out);
-int hana_host_free(void* p);
+HANA_API int hana_host_alloc(size_t bytes, void** out);
+HANA_API int hana_host_free(void* p);
 
 /* --- stage-level entry points (parity tests, SURVEY.md §4 tier 1) --------- */
 /* Runs only the vertex kernel; out_v2f receives ncorners records of
  * shader_struct_v2f (IShader.h:41-47): 13 floats each. Fields the shader
  * does not set are written as 0. */
-int hana_stage_vertex(hana_ctx* ctx, const hana_model* model, int shader_id,
+HANA_API int hana_stage_vertex(hana_ctx* ctx, const hana_model* model, int shader_id,
                       const HanaUniforms* uniforms, float* out_v2f_host);
 /* Runs vertex + clip + cull + setup for a `width` x `height` target and
  * returns the surviving triangles sorted by order key: per triangle
  * 1 order key (face*8 + fan index) in out_order, and 3x13 floats of the
  * post-clip v2f records in out_v2f (capacity in triangles). */
-int hana_stage_setup(hana_ctx* ctx, const hana_model* model, int shader_id,
+HANA_API int hana_stage_setup(hana_ctx* ctx, const hana_model* model, int shader_id,
                      const HanaUniforms* uniforms, int width, int height, int capacity,
                      uint32_t* out_order, float* out_v2f, int* out_count);
 /* Primitive-ID buffer of the last hana_draw on `rb` is not kept by the
  * reference; this variant of hana_draw also writes, per pixel, the order key
  * of the primitive that owns it (0xFFFFFFFF where the draw wrote nothing). */
-int hana_draw_primid(hana_ctx* ctx, hana_rb* rb, const hana_model* model, int shader_id,
+HANA_API int hana_draw_primid(hana_ctx* ctx, hana_rb* rb, const hana_model* model, int shader_id,
                      const HanaUniforms* uniforms, const hana_texture* diffuse,
                      const hana_texture* normal, const hana_rb* shadow_map,
                      uint32_t* out_primid_host);
