@@ -462,8 +462,9 @@ __global__ void __launch_bounds__(RASTER_THREADS)
         if (MODE != MODE_RMW && wid == 1 && !clear_done) clear_done = clear_slots<MODE>(q, sm, tm_color, tm_depth, tm_r8, n_slots);
 
         /* -- one non-empty tile -- */
-        const int f = (int)(it >> TILE_BITS);
-        const int t = (int)(it & TILE_MASK);
+        const uint32_t item = p.work[it];
+        const int f = (int)(item >> TILE_BITS);
+        const int t = (int)(item & TILE_MASK);
         const int tx = t % p.tiles_x, ty = t / p.tiles_x;
         const int px = tx * TILE + lx, py = ty * TILE + ly;
         const bool in_frame = px < p.W && py < p.H;

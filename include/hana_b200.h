@@ -238,6 +238,41 @@ HANA_API int hana_sweep_stats(hana_sweep* s, int frame, HanaStats* out); /* sync
 HANA_API int hana_host_alloc(size_t bytes, void** out);
 HANA_API int hana_host_free(void* p);
 
+/* --- host-side mirror of the path's caller ---------------- */
+/* Camera (camera.h:13-33) and the per-draw constants of SingleModelScene /
+ * DrawModel (scene.cpp:7,77-84; scene.h:8-9; gameobject.cpp:12-17), as PODs. */
+typedef struct HanaCamera {
+    float position[3];
+    float target[3];
+    float aspect;
+} HanaCamera;
+typedef struct HanaSceneDesc {
+    float light_pos[3];
+    float model_pos[3];
+    float model_rot_deg[3];
+    float model_scale[3];
+    float light_color[4];
+    float ambient[4];
+    float mat_color[4];
+    float mat_specular[4];
+    float gloss;
+    float bump_scale;
+} HanaSceneDesc;
+HANA_API int hana_camera_init(HanaCamera* cam, const float position[3], const float target[3], float aspect);
+/* Camera::update_transform(Motion) camera.cpp:63-70 */
+HANA_API int hana_camera_update(HanaCamera* cam, float orbit_x, float orbit_y, float pan_x, float pan_y, float dolly);
+/* light (2,2,2), identity model transform, LightColor/AMBIENT, white material, gloss 50, bump 1 */
+HANA_API int hana_scene_defaults(HanaSceneDesc* s);
+/* The ShaderData block DrawModel::draw builds before its passes (scene.h:55-71),
+ * bit-identical to the reference's for the same camera (host float arithmetic in
+ * the reference's evaluation order). */
+HANA_API int hana_scene_uniforms(const HanaCamera* cam, const HanaSceneDesc* s, int width, int height, int enable_shadow,
+                                 HanaUniforms* out);
+/* BASELINE.json configs[2]: frame k of the orbit sweep = Camera(CAMERA_POSITION,
+ * CAMERA_TARGET, W/H) advanced k times by orbit (1/frames_per_turn, 0). */
+HANA_API int hana_orbit_sweep_uniforms(const HanaSceneDesc* s, int width, int height, int enable_shadow, int first, int count,
+                                       int frames_per_turn, HanaUniforms* out);
+
 /* --- stage-level entry points (parity tests, SURVEY.md §4 tier 1) --------- */
 /* Runs only the vertex kernel; out_v2f receives ncorners records of
  * shader_struct_v2f (IShader.h:41-47): 13 floats each. Fields the shader

@@ -43,7 +43,6 @@ int emu_coverage(const float* abc6, int W, int H, int px, int py, float* w3) {
     float s1x = abc6[5] - abc6[1], s1y = abc6[3] - abc6[1];
     float uz = s0x * s1y - s0y * s1x;
     if (!(fabsf(uz) > 0.01f)) return 0;
-    if (uz < 0) { s0x = -s0x; s0y = -s0y; s1x = -s1x; s1y = -s1y; uz = -uz; }
     float ux, uy;
     bool in = coverage_test(abc6[0], abc6[1], s0x, s0y, s1x, s1y, uz, (float)px, (float)py, ux, uy);
     barycentric_weights(ux, uy, uz, w3[0], w3[1], w3[2]);
