@@ -1,0 +1,372 @@
+#!/usr/bin/env python
+"""bench.py — the rasterisation hot path on N B200s, one JSON line on rank 0.
+
+A step = one batch of FRAMES_PER_STEP 1080p frames of BASELINE.json configs[1] (african_head, ShadowShader
+pass + Blinn pass, 1920x1080), each frame from the next camera of the configs[2] orbit (1024 cameras per turn,
+the reference's own Camera::update_transform). Frames are sharded over ranks in contiguous blocks of the orbit,
+no collective on the data path (weak scaling: every rank renders FRAMES_PER_STEP frames per step).
+
+  value : frames/s, whole job, uniforms already resident in HBM, frames left in HBM (CUDA events, max over ranks)
+  e2e   : frames/s through the C ABI with HOST buffers: per step the uniforms go host->device from pinned memory
+          and every frame's colour + depth come back device->host into pinned memory, all inside the timed region
+  roofline     : the dominant kernel (raster_main), algorithmic bytes / its CUDA-event time, vs MEASURED_PEAKS.json
+  cpu_baseline : the reference's own CPU pipeline (oracle/_ref, built from the unmodified sources) on the host cores
+
+--impl reference times only that CPU pipeline, with every host core, on a bounded sample of the same frames.
+"""
+import argparse
+import ctypes as C
+import json
+import multiprocessing as mp
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+W, H = 1920, 1080
+FRAMES_PER_STEP = 64
+ORBIT = 1024
+SCENE = "african_head"
+T_BLINN = 7  # texel bytes per main-pass fragment: 3 (diffuse BGR) + 4 (shadow-map RGBA8 texel), SURVEY.md §8(d)
+METRIC = "frames/s at 1080p, shadowed Blinn (ShadowShader pass + BlinnShader pass), african_head orbit sweep"
+
+
+def env_int(name, default):
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
+def host_cores():
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
+# ----------------------------------------------------------------------------- reference / cpu baseline
+def _ref_worker(args):
+    """One process = one instance of the reference (it is single-threaded and not re-entrant)."""
+    obj, first, count, orbit = args
+    from oracle import horacle as Hh
+    ref = Hh.Reference(obj, W, H, Hh.BLINN, instrumented=False)
+    for _ in range(first):
+        ref.camera_motion(orbit=(1.0 / orbit, 0))
+    ref.warmup(True)
+    t = 0.0
+    for _ in range(count):
+        t += ref.render_time(True)  # DrawModel::draw only: both passes + shadow-map clear
+        ref.camera_motion(orbit=(1.0 / orbit, 0))
+    ref.close()
+    return t
+
+
+def _port_worker(args):
+    pack, first, count, orbit = args
+    import __graft_entry__ as ge
+    hana = ge.load_package()
+    from oracle import horacle as Hh
+    sc = hana.load_hscene(pack) if pack else hana.synthetic_scene("blob", tex=1024)
+    port = Hh.Port()
+    arr = hana.orbit_sweep_uniforms(W, H, first, count, frames_per_turn=orbit)
+    t = 0.0
+    for k in range(count):
+        u = Hh.HanaUniforms.from_bytes(arr[k].to_bytes())
+        t0 = time.perf_counter()
+        port.draw_model(Hh.BLINN, u, sc.a2v, W, H, diffuse=sc.diffuse, normal=sc.normal)
+        t += time.perf_counter() - t0
+    return t
+
+
+def cpu_frames_per_s(frames_per_core, first_frame=0):
+    """Frame-sharded run of the CPU pipeline over all host cores. Returns (frames/s, kind, cores, sample)."""
+    cores = host_cores()
+    obj = os.path.join(ROOT, "oracle", "_ref", "assets", SCENE, SCENE + ".obj")
+    pack = os.path.join(ROOT, "oracle", "_ref", "assets", SCENE + ".npz")
+    use_ref = os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libhana_ref.so")) and os.path.exists(obj)
+    stride = ORBIT // cores if cores <= ORBIT else 1
+    jobs = [((obj if use_ref else (pack if os.path.exists(pack) else None)), (first_frame + i * stride) % ORBIT, frames_per_core,
+             ORBIT) for i in range(cores)]
+    ctx = mp.get_context("spawn")
+    t0 = time.perf_counter()
+    with ctx.Pool(cores) as pool:
+        busy = pool.map(_ref_worker if use_ref else _port_worker, jobs)
+    wall = time.perf_counter() - t0
+    n = cores * frames_per_core
+    # throughput of the parallel section: every core renders its block concurrently; the slowest core bounds it
+    fps = n / max(busy)
+    kind = "reference" if use_ref else "port"
+    sample = "%d frames of the orbit (%d per core x %d cores, DrawModel::draw only: both passes + shadow clear), wall %.1fs" % (
+        n, frames_per_core, cores, wall)
+    return fps, kind, cores, sample, statistics.mean(busy) / frames_per_core
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return 0
+    per_core = 2
+    fps_steps = []
+    for _ in range(args.warmup if args.warmup < 2 else 1):
+        cpu_frames_per_s(1)
+    info = None
+    for s in range(args.steps):
+        info = cpu_frames_per_s(per_core, first_frame=(s * 37) % ORBIT)
+        fps_steps.append(info[0])
+    fps = statistics.mean(fps_steps)
+    _, kind, cores, sample, sec_per_frame_core = info
+    line = {
+        "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * cores * per_core / fps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "bundled african_head scene, orbit cameras",
+        "config": {"workload": "configs[1] frames (african_head, Shadow+Blinn two-pass, 1920x1080) on the configs[2] orbit cameras; "
+                               "CPU reference, frame-sharded over host cores", "frames_per_step": cores * per_core},
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": kind, "sample": sample,
+                         "single_core_ms_per_frame": 1e3 * sec_per_frame_core},
+        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows = []
+        self.proc = None
+        self.idx = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = float(r[1])
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except (ValueError, IndexError):
+                pass
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------- GPU arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="hana")
+    ap.add_argument("--frames", type=int, default=FRAMES_PER_STEP)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    if args.impl == "reference":
+        return run_reference(args, rank)
+    args.warmup = max(args.warmup, 3)
+
+    import torch
+    import torch.distributed as dist
+
+    import __graft_entry__ as ge
+    hana = ge.load_package()
+    from hana_softwarerenderer_b200.api import PinnedBuffer, HanaUniforms
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    F = args.frames
+    ctx = hana.Context(local)
+    pack = os.path.join(ROOT, "oracle", "_ref", "assets", SCENE + ".npz")
+    if os.path.exists(pack):
+        scene, data = hana.load_hscene(pack), "bundled african_head mesh + textures (reference assets), synthetic orbit cameras"
+    else:
+        scene, data = hana.synthetic_scene("blob", tex=1024), "synthetic sphere scene (bundled assets not packed on this box)"
+    model, dtex, ntex = scene.upload(ctx)
+    sweep = ctx.sweep(W, H, F)
+
+    # this rank's contiguous block of the orbit; step s renders frames [s*F, (s+1)*F) of the block (cyclic)
+    block = ORBIT // world
+    first = rank * block
+    total_steps = args.warmup + args.steps
+    usz = C.sizeof(HanaUniforms)
+    pinned_u = PinnedBuffer(usz * F * total_steps)
+    for s in range(total_steps):
+        arr = hana.orbit_sweep_uniforms(W, H, first + (s * F) % block, F, frames_per_turn=ORBIT)
+        C.memmove(pinned_u.ptr + s * F * usz, arr, usz * F)
+    u_dev = torch.empty(usz * F * total_steps, dtype=torch.uint8, device="cuda")
+    u_dev.copy_(torch.from_numpy(pinned_u.array))
+    torch.cuda.synchronize()
+
+    def barrier():
+        ctx.sync()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    def step_resident(s):
+        clr = (C.c_uint8 * 4)(0, 0, 0, 1)
+        r = ctx.L.hana_sweep_render_dev(sweep.h, model.h, hana.BLINN, C.c_void_p(u_dev.data_ptr() + s * F * usz), F, dtex.h, ntex.h,
+                                        clr, float(hana.FLT_MAX))
+        if r != 0:
+            raise hana.HanaError(r, ctx.L.hana_last_error().decode())
+
+    # ---- value: device-resident inputs, frames stay in HBM
+    for s in range(args.warmup):
+        step_resident(s)
+    barrier()
+    ctx.profile(True, reset=True)
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    l0 = ctx.launches
+    ctx.timer_start()
+    for s in range(args.warmup, total_steps):
+        step_resident(s)
+    ms = ctx.timer_stop()
+    barrier()
+    clk = clocks.stop() if rank == 0 else None
+    launches = ctx.launches - l0
+    prof = ctx.profile_get()
+    ctx.profile(False, reset=False)
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    frames_total = F * args.steps * world
+    value = frames_total / (ms_max * 1e-3)
+
+    # ---- e2e: host uniforms in (pinned), colour + depth of every frame out (pinned), inside the timed region
+    npx = W * H
+    pin_c = PinnedBuffer(npx * 4 * F)
+    pin_d = PinnedBuffer(npx * 4 * F)
+
+    def step_e2e(s):
+        clr = (C.c_uint8 * 4)(0, 0, 0, 1)
+        r = ctx.L.hana_sweep_render(sweep.h, model.h, hana.BLINN, C.c_void_p(pinned_u.ptr + s * F * usz), F, dtex.h, ntex.h, clr,
+                                    float(hana.FLT_MAX))
+        if r != 0:
+            raise hana.HanaError(r, ctx.L.hana_last_error().decode())
+        sweep.download_async(0, F, pin_c.ptr, pin_d.ptr)
+        ctx.sync()  # the host owns the frames now
+
+    for s in range(min(2, args.warmup)):
+        step_e2e(s)
+    barrier()
+    ctx.timer_start()
+    for s in range(args.warmup, total_steps):
+        step_e2e(s)
+    ms_e2e = ctx.timer_stop()
+    barrier()
+    t = torch.tensor([ms_e2e], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = frames_total / (float(t.item()) * 1e-3)
+    sums_ok = int(np.frombuffer(pin_d.array, np.float32, count=npx).min() < 1.0)  # something was drawn
+
+    if rank == 0:
+        peaks, peak_src = None, "fallback"
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+            peak, peak_src = float(peaks["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except (OSError, KeyError, ValueError):
+            peak = 6650.0
+        # reference-equivalent fragment counts: sampled with the instrumented CPU port
+        cpu = None
+        frag_main = frag_all = None
+        if world == 1 and not args.no_cpu_baseline:
+            from oracle import horacle as Hh
+            port = Hh.Port()
+            fm, fa = [], []
+            for k in (0, 256, 512, 768):
+                u = Hh.HanaUniforms.from_bytes(hana.orbit_sweep_uniforms(W, H, k, 1, frames_per_turn=ORBIT)[0].to_bytes())
+                r = port.draw_model(Hh.BLINN, u, scene.a2v, W, H, diffuse=scene.diffuse, normal=scene.normal, want_counters=True)
+                fm.append(r["counters"][1]["zpass"])
+                fa.append(r["counters"][0]["zpass"] + r["counters"][1]["zpass"])
+            frag_main, frag_all = statistics.mean(fm), statistics.mean(fa)
+            fps, kind, cores, sample, spf = cpu_frames_per_s(2)
+            cpu = {"value": fps, "unit": "frames/s", "cores": cores, "kind": kind, "sample": sample,
+                   "single_core_ms_per_frame": 1e3 * spf}
+        if frag_main is None:
+            frag_main, frag_all = 436951.0, 997805.0  # camera 0 of the orbit
+        ncorner = scene.a2v.shape[0]
+        bytes_frame = 2 * (ncorner * 32 + npx * 8) + frag_main * T_BLINN          # whole frame, both passes
+        bytes_raster_main = npx * 8 + frag_main * T_BLINN                        # the dominant kernel's share
+        rm_ms, rm_n = prof["raster_main"]
+        per_launch_ms = rm_ms / max(rm_n, 1)
+        achieved = bytes_raster_main * F / (per_launch_ms * 1e-3) / 1e9
+        kernel_ms = {k: v[0] for k, v in prof.items()}
+        gpu_ms_step = sum(kernel_ms.values()) / args.steps
+        line = {
+            "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": data,
+            "config": {"workload": "configs[1] frames (african_head, Shadow+Blinn two-pass, 1920x1080) on the configs[2] orbit cameras, "
+                                   "batched %d frames per submission" % F,
+                       "frames_per_step": F, "width": W, "height": H, "faces": ncorner // 3, "orbit_frames": ORBIT,
+                       "sharding": "contiguous orbit blocks per rank, no collective",
+                       "l2": "per-step footprint %.2f GB of frame targets >> 126 MB L2; mesh + textures (%.1f MB) are reused by "
+                             "design" % (F * npx * 9 / 1e9, (ncorner * 32 + 2 * 4 * 1024 * 1024) / 1e6),
+                       "tma": bool(ctx.uses_tma)},
+            "mfrag_per_s": value * frag_all / 1e6, "mtri_per_s": value * 2 * (ncorner // 3) / 1e6,
+            "us_per_frame": 1e6 / value * world,
+            "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": usz * F, "d2h_bytes_per_step": npx * 8 * F,
+                    "note": "hana_sweep_render from pinned host uniforms + colour and depth of every frame copied back to pinned host "
+                            "memory; PCIe-bound", "frames_checked": sums_ok},
+            "gpu_launches": int(launches),
+            "clocks": clk,
+            "roofline": {"bound": "hbm", "kernel": "raster_kernel<BLINN, CLEAR_FOLD>", "achieved": achieved, "peak": peak,
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": bytes_raster_main * F, "ms_per_launch": per_launch_ms},
+            "frame_roofline": {"algorithmic_bytes_per_frame": bytes_frame, "achieved": bytes_frame * F / (gpu_ms_step * 1e-3) / 1e9,
+                               "frac": bytes_frame * F / (gpu_ms_step * 1e-3) / 1e9 / peak, "unit": "GB/s",
+                               "note": "SURVEY.md §8(d) bytes of the whole frame over the summed kernel time of a step"},
+            "kernel_ms_per_step": {k: v / args.steps for k, v in kernel_ms.items()},
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line))
+    for o in (sweep, model, dtex, ntex):
+        o.close()
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
