@@ -52,7 +52,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 enum ProfKind { PROF_BEGIN = 0, PROF_SETUP, PROF_SCAN, PROF_FILL, PROF_RASTER_SHADOW, PROF_RASTER_MAIN, PROF_OTHER, PROF_KINDS };
 
 struct Scratch {
-    TriRecord* tri_rec = nullptr;
+    float4* tri_rec = nullptr; /* 4 float4 per record */
     float4* tri_attr = nullptr;
     size_t tri_total = 0; /* records allocated (n_frames * tri_cap) */
     size_t attr_total = 0;
@@ -60,9 +60,9 @@ struct Scratch {
     size_t frames_cap = 0;
     uint32_t* tile_arrays = nullptr; /* count | cursor | offset, each n_frames * n_tiles */
     size_t tile_arr_cap = 0;
-    uint32_t* refs = nullptr;
-    size_t pool_cap = 0;
-    uint32_t* work = nullptr;
+    float4* tile_recs = nullptr; /* pool of raster records: 4 float4 each */
+    size_t pool_cap = 0;         /* float4 elements */
+    uint4* work = nullptr;
     size_t work_cap = 0;
     PassCounters* counters = nullptr;
     PassCounters* counters_host = nullptr; /* pinned */
@@ -231,7 +231,7 @@ extern "C" int hana_ctx_destroy(hana_ctx* ctx) {
     if (ctx->host_shadow) hana_rb_destroy(ctx->host_shadow);
     Scratch& s = ctx->sc;
     cudaFree(s.tri_rec); cudaFree(s.tri_attr); cudaFree(s.tri_count); cudaFree(s.tile_arrays);
-    cudaFree(s.refs); cudaFree(s.work); cudaFree(s.counters); cudaFreeHost(s.counters_host);
+    cudaFree(s.tile_recs); cudaFree(s.work); cudaFree(s.counters); cudaFreeHost(s.counters_host);
     cudaFree(ctx->u_raw); cudaFree(ctx->u_dev); cudaFree(ctx->stat_pixels);
     for (auto& p : ctx->prof_pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
     for (auto e : ctx->ev_pool) cudaEventDestroy(e);
@@ -602,7 +602,7 @@ static int run_pass(hana_ctx* ctx, const PassDesc& d) {
         return fail(HANA_E_INVALID, "R8 targets take the ShadowShader only");
     const int tiles_x = (d.W + TILE - 1) / TILE, tiles_y = (d.H + TILE - 1) / TILE;
     const size_t n_tiles = (size_t)tiles_x * tiles_y;
-    if (n_tiles > TILE_MASK) return fail(HANA_E_INVALID, "too many screen tiles");
+    if (tiles_x > 1024 || tiles_y > 1024) return fail(HANA_E_INVALID, "target larger than 16384 pixels on a side");
     if (d.n_frames < 1 || d.n_frames > 4096) return fail(HANA_E_INVALID, "1..4096 frames per batch");
     const int nfaces = d.model->ncorners / 3;
     Scratch& sc = ctx->sc;
@@ -618,12 +618,12 @@ static int run_pass(hana_ctx* ctx, const PassDesc& d) {
     for (int attempt = 0; attempt < 4 && !lists_ready; attempt++) {
         /* capacities */
         size_t tri_total = (size_t)tri_cap * d.n_frames;
-        HANA_TRY(grow(&sc.tri_rec, &sc.tri_total, tri_total, ctx));
-        HANA_TRY(grow(&sc.tri_attr, &sc.attr_total, tri_total * 6, ctx));
+        HANA_TRY(grow(&sc.tri_rec, &sc.tri_total, tri_total * 4, ctx));
+        HANA_TRY(grow(&sc.tri_attr, &sc.attr_total, tri_total * MAX_ATTR_QUADS, ctx));
         HANA_TRY(grow(&sc.tri_count, &sc.frames_cap, (size_t)d.n_frames, ctx));
         HANA_TRY(grow(&sc.tile_arrays, &sc.tile_arr_cap, tiles_total * 3, ctx));
         HANA_TRY(grow(&sc.work, &sc.work_cap, tiles_total, ctx));
-        if (!sc.refs) HANA_TRY(grow(&sc.refs, &sc.pool_cap, std::max<size_t>(tri_total * 8, 65536), ctx));
+        if (!sc.tile_recs) HANA_TRY(grow(&sc.tile_recs, &sc.pool_cap, std::max<size_t>(tri_total * 8, 65536) * 4, ctx));
 
         p.posu = d.model->posu;
         p.nrmv = d.model->nrmv;
@@ -642,8 +642,8 @@ static int run_pass(hana_ctx* ctx, const PassDesc& d) {
         p.tile_count = sc.tile_arrays;
         p.tile_cursor = sc.tile_arrays + tiles_total;
         p.tile_offset = sc.tile_arrays + 2 * tiles_total;
-        p.refs = sc.refs;
-        p.pool_cap = (uint32_t)std::min<size_t>(sc.pool_cap, 0xFFFFFFFFull);
+        p.tile_recs = sc.tile_recs;
+        p.pool_cap = (uint32_t)std::min<size_t>(sc.pool_cap / 4, 0xFFFFFFFFull);
         p.work = sc.work;
         p.counters = sc.counters;
         p.dbg_v2f = d.dbg_v2f;
@@ -687,10 +687,10 @@ static int run_pass(hana_ctx* ctx, const PassDesc& d) {
             ctx->tri_cap_hint = std::max(ctx->tri_cap_hint, tri_cap);
             continue; /* triangles were dropped: redo setup with room for all of them */
         }
-        if ((size_t)c.pool_used > sc.pool_cap) {
-            HANA_TRY(grow(&sc.refs, &sc.pool_cap, (size_t)c.pool_used + c.pool_used / 8, ctx));
-            p.refs = sc.refs;
-            p.pool_cap = (uint32_t)std::min<size_t>(sc.pool_cap, 0xFFFFFFFFull);
+        if ((size_t)c.pool_used > sc.pool_cap / 4) {
+            HANA_TRY(grow(&sc.tile_recs, &sc.pool_cap, ((size_t)c.pool_used + c.pool_used / 8) * 4, ctx));
+            p.tile_recs = sc.tile_recs;
+            p.pool_cap = (uint32_t)std::min<size_t>(sc.pool_cap / 4, 0xFFFFFFFFull);
         }
         lists_ready = true;
     }
@@ -1227,20 +1227,25 @@ extern "C" int hana_stage_setup(hana_ctx* ctx, const hana_model* model, int shad
         return r;
     }
     uint32_t n = tri_counts.empty() ? 0 : tri_counts[0];
-    std::vector<TriRecord> recs(n);
+    std::vector<float> recs((size_t)n * 16);
     std::vector<float> v2f((size_t)n * 39);
     cudaError_t e = cudaSuccess;
     if (n) {
-        e = cudaMemcpy(recs.data(), ctx->sc.tri_rec, sizeof(TriRecord) * n, cudaMemcpyDeviceToHost);
+        e = cudaMemcpy(recs.data(), ctx->sc.tri_rec, sizeof(float) * 16 * n, cudaMemcpyDeviceToHost);
         if (e == cudaSuccess) e = cudaMemcpy(v2f.data(), dbg, (size_t)n * 39 * 4, cudaMemcpyDeviceToHost);
     }
     cudaFree(dbg);
     if (e != cudaSuccess) return fail(HANA_E_CUDA, cudaGetErrorString(e));
     std::vector<uint32_t> idx(n);
     for (uint32_t i = 0; i < n; i++) idx[i] = i;
-    std::sort(idx.begin(), idx.end(), [&](uint32_t a, uint32_t b) { return recs[a].key < recs[b].key; });
+    auto key_of = [&](uint32_t i) {
+        uint32_t k;
+        memcpy(&k, &recs[(size_t)i * 16 + 11], 4);
+        return k;
+    };
+    std::sort(idx.begin(), idx.end(), [&](uint32_t a, uint32_t b) { return key_of(a) < key_of(b); });
     for (uint32_t i = 0; i < n; i++) {
-        out_order[i] = recs[idx[i]].key;
+        out_order[i] = key_of(idx[i]);
         memcpy(out_v2f + (size_t)i * 39, v2f.data() + (size_t)idx[i] * 39, 39 * 4);
     }
     *out_count = (int)n;

@@ -5,7 +5,7 @@
  *   setup_kernel   vertex shading + homogeneous clip + cull + triangle setup, warp-scan
  *                  compaction of the surviving triangles, per-tile reference counts
  *   scan_kernel    exclusive scan of the tile counts -> list offsets + non-empty tile queue
- *   fill_kernel    triangle indices into the per-tile lists
+ *   fill_kernel    triangle raster records copied into the per-tile lists (no indirection in the rasteriser)
  *   raster_kernel  persistent CTAs, one 16x16 tile at a time: coverage + depth resolve in
  *                  registers, shading of the winning fragment, tile flush by TMA store;
  *                  empty tiles are cleared by fire-and-forget TMA stores from a constant tile
@@ -34,8 +34,9 @@ constexpr int TILE = 16;             /* screen tile edge (pixels) */
 constexpr int TILE_PIX = TILE * TILE;
 constexpr int RASTER_THREADS = 256;  /* one thread per tile pixel */
 constexpr int CHUNK = 64;            /* triangles staged in shared memory per round */
-constexpr int TILE_BITS = 20;        /* work item = frame << 20 | tile */
+constexpr int TILE_BITS = 20;        /* work item = frame << 20 | tile_y << 10 | tile_x */
 constexpr uint32_t TILE_MASK = (1u << TILE_BITS) - 1u;
+constexpr uint32_t WORK_INVALID = 0xFFFFFFFFu;
 constexpr int SETUP_THREADS = 128;
 constexpr int SCAN_THREADS = 1024;
 
@@ -65,16 +66,16 @@ struct PassParams {
     int W, H, tiles_x, tiles_y, n_tiles;
     const DevUniforms* uniforms; /* [n_frames] */
     /* scratch */
-    TriRecord* tri_rec;   /* [n_frames][tri_cap] */
+    float4* tri_rec;      /* [n_frames][tri_cap][4]: raster records */
     float4* tri_attr;     /* [n_frames][tri_cap][attr_quads] */
     uint32_t tri_cap;
     uint32_t* tri_count;  /* [n_frames] */
     uint32_t* tile_count; /* [n_frames][n_tiles] */
     uint32_t* tile_offset;
     uint32_t* tile_cursor;
-    uint32_t* refs;       /* pool */
-    uint32_t pool_cap;
-    uint32_t* work;       /* [n_frames*n_tiles] */
+    float4* tile_recs;    /* pool of raster records (4 x float4 each), grouped per (frame, tile) */
+    uint32_t pool_cap;    /* in records */
+    uint4* work;          /* [n_frames*n_tiles] non-empty tiles: {item, count, offset, 0} */
     PassCounters* counters;
     float* dbg_v2f;       /* optional: [tri_cap][39] post-clip v2f of frame 0 (stage tests) */
 };
@@ -155,19 +156,31 @@ __global__ void vertex_kernel(const float4* __restrict__ posu, const float4* __r
 }
 
 /* ---- setup ------------------------------------------------------------------ */
+/* attribute floats a shader's fragment() reads / float4 chunks of the per-triangle attribute block
+ * (chunk 0 = the three 1/w of graphics.cpp:336, then 3 floats per attribute) */
+template <int SHADER>
+struct ShaderAttrs {
+    static constexpr int NA = (SHADER == HANA_SHADER_SHADOW || SHADER == HANA_SHADER_GROUND || SHADER == HANA_SHADER_TOON)
+                                  ? 1
+                                  : (SHADER == HANA_SHADER_TEXTURE ? 2 : (SHADER == HANA_SHADER_TEXTURE_LIGHT ? 5 : 8));
+    static constexpr int NQ = 1 + (3 * NA + 3) / 4;
+};
+constexpr int MAX_ATTR_QUADS = 7;
+
+/* Raster record in memory, 4 x float4:
+ *   q0 = ax, ay, s0x, s0y      q1 = s1x, s1y, uz, 1/uz
+ *   q2 = bbx, bby, triangle index (attribute block), order key      q3 = d0, d1, d2, |uz| * 2^-24 */
 template <int SHADER>
 __device__ __forceinline__ void store_triangle(const PassParams& p, int f, uint32_t slot, const TriRecord& r,
                                                const float* v0, const float* v1, const float* v2) {
-    constexpr int NA = (SHADER == HANA_SHADER_SHADOW || SHADER == HANA_SHADER_GROUND || SHADER == HANA_SHADER_TOON)
-                           ? 1
-                           : (SHADER == HANA_SHADER_TEXTURE ? 2 : (SHADER == HANA_SHADER_TEXTURE_LIGHT ? 5 : 8));
-    constexpr int NQ = (3 * NA + 3) / 4;
-    float4* dst = reinterpret_cast<float4*>(p.tri_rec + (size_t)f * p.tri_cap + slot);
+    constexpr int NA = ShaderAttrs<SHADER>::NA;
+    constexpr int NQ = ShaderAttrs<SHADER>::NQ;
+    float4* dst = p.tri_rec + ((size_t)f * p.tri_cap + slot) * 4;
     dst[0] = make_float4(r.ax, r.ay, r.s0x, r.s0y);
-    dst[1] = make_float4(r.s1x, r.s1y, r.uz, __uint_as_float(r.bbx));
-    dst[2] = make_float4(__uint_as_float(r.bby), r.d0, r.d1, r.d2);
-    dst[3] = make_float4(r.rw0, r.rw1, r.rw2, __uint_as_float(r.key));
-    float a[NQ * 4];
+    dst[1] = make_float4(r.s1x, r.s1y, r.uz, r.ruz);
+    dst[2] = make_float4(__uint_as_float(r.bbx), __uint_as_float(r.bby), __uint_as_float(slot), __uint_as_float(r.key));
+    dst[3] = make_float4(r.d0, r.d1, r.d2, r.thr);
+    float a[(NQ - 1) * 4];
 #pragma unroll
     for (int k = 0; k < NA; k++) {
         const int src = shader_attr_src(SHADER, k);
@@ -176,10 +189,11 @@ __device__ __forceinline__ void store_triangle(const PassParams& p, int f, uint3
         a[3 * k + 2] = v2[src];
     }
 #pragma unroll
-    for (int k = 3 * NA; k < NQ * 4; k++) a[k] = 0.f;
+    for (int k = 3 * NA; k < (NQ - 1) * 4; k++) a[k] = 0.f;
     float4* ad = p.tri_attr + ((size_t)f * p.tri_cap + slot) * NQ;
+    ad[0] = make_float4(r.rw0, r.rw1, r.rw2, 0.f);
 #pragma unroll
-    for (int q = 0; q < NQ; q++) ad[q] = make_float4(a[4 * q], a[4 * q + 1], a[4 * q + 2], a[4 * q + 3]);
+    for (int q = 1; q < NQ; q++) ad[q] = make_float4(a[4 * q - 4], a[4 * q - 3], a[4 * q - 2], a[4 * q - 1]);
     if (p.dbg_v2f && f == 0) {
         float* d = p.dbg_v2f + (size_t)slot * 39;
         for (int k = 0; k < V2F_N; k++) {
@@ -322,12 +336,15 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_kernel(PassParams p) {
     for (int t = t0; t < t1; t++) {
         uint32_t c = tc[t];
         to[t] = off;
+        if (c) {
+            uint32_t tx = (uint32_t)(t % p.tiles_x), ty = (uint32_t)(t / p.tiles_x);
+            p.work[wi++] = make_uint4(((uint32_t)f << TILE_BITS) | (ty << 10) | tx, c, off, 0u);
+        }
         off += c;
-        if (c) p.work[wi++] = ((uint32_t)f << TILE_BITS) | (uint32_t)t;
     }
 }
 
-/* ---- fill: triangle indices into the tile lists ----------------------------- */
+/* ---- fill: raster records into the tile lists --------------------------------- */
 __global__ void __launch_bounds__(256) fill_kernel(PassParams p) {
     const int f = blockIdx.y;
     const uint32_t i = blockIdx.x * 256u + threadIdx.x;
@@ -335,9 +352,10 @@ __global__ void __launch_bounds__(256) fill_kernel(PassParams p) {
     if (n > p.tri_cap) n = p.tri_cap;
     if (i >= n) return;
     if (p.counters->pool_used > p.pool_cap) return; /* host re-runs the pass with a larger pool */
-    const float4* rec = reinterpret_cast<const float4*>(p.tri_rec + (size_t)f * p.tri_cap + i);
-    uint32_t bbx = __float_as_uint(__ldg(rec + 1).w);
-    uint32_t bby = __float_as_uint(__ldg(rec + 2).x);
+    const float4* rec = p.tri_rec + ((size_t)f * p.tri_cap + i) * 4;
+    const float4 q0 = __ldg(rec), q1 = __ldg(rec + 1), q2 = __ldg(rec + 2), q3 = __ldg(rec + 3);
+    uint32_t bbx = __float_as_uint(q2.x);
+    uint32_t bby = __float_as_uint(q2.y);
     int tx0 = (int)(bbx & 0xFFFFu) >> 4, tx1 = (int)(bbx >> 16) >> 4;
     int ty0 = (int)(bby & 0xFFFFu) >> 4, ty1 = (int)(bby >> 16) >> 4;
     uint32_t* cur = p.tile_cursor + (size_t)f * p.n_tiles;
@@ -346,7 +364,11 @@ __global__ void __launch_bounds__(256) fill_kernel(PassParams p) {
         for (int tx = tx0; tx <= tx1; tx++) {
             int t = ty * p.tiles_x + tx;
             uint32_t s = atomicAdd(cur + t, 1u);
-            p.refs[to[t] + s] = i;
+            float4* d = p.tile_recs + ((size_t)to[t] + s) * 4;
+            d[0] = q0;
+            d[1] = q1;
+            d[2] = q2;
+            d[3] = q3;
         }
 }
 
@@ -356,13 +378,13 @@ struct alignas(128) RasterSmem {
     float out_depth[TILE_PIX];
     uint32_t clr_color[TILE_PIX]; /* constant clear tiles, TMA store source for empty tiles */
     float clr_depth[TILE_PIX];
-    float4 tri[CHUNK * 4];        /* staged TriRecords */
-    uint32_t tri_idx[CHUNK];
+    float4 tri[CHUNK * 4];        /* staged raster records */
+    uint32_t bbx[CHUNK];          /* their pixel ranges, conflict-free for the per-warp overlap test */
+    uint32_t bby[CHUNK];
     alignas(128) uint8_t out_r8[TILE_PIX]; /* MODE_SHADOW_R8 tile, box 16x16 u8 */
     alignas(128) uint8_t clr_r8[TILE_PIX];
+    alignas(16) uint4 cur;        /* the work entry being processed: {item, count, offset, -} */
     alignas(8) uint64_t bar;
-    uint32_t item;
-    uint32_t clear_base;
 };
 
 /* One warp claims 32 consecutive (frame,tile) slots and clears those no triangle touches:
@@ -410,14 +432,17 @@ __device__ __forceinline__ bool clear_slots(const RasterParams& q, RasterSmem& s
     return false;
 }
 
+__device__ __forceinline__ uint4 fetch_work(const PassParams& p, uint32_t idx, uint32_t n_work) {
+    if (idx < n_work) return __ldg(p.work + idx);
+    return make_uint4(WORK_INVALID, 0u, 0u, 0u);
+}
+
 template <int SHADER, int MODE>
 __global__ void __launch_bounds__(RASTER_THREADS)
     raster_kernel(RasterParams q, const __grid_constant__ CUtensorMap tm_color, const __grid_constant__ CUtensorMap tm_depth,
                   const __grid_constant__ CUtensorMap tm_r8) {
-    constexpr int NA = (SHADER == HANA_SHADER_SHADOW || SHADER == HANA_SHADER_GROUND || SHADER == HANA_SHADER_TOON)
-                           ? 1
-                           : (SHADER == HANA_SHADER_TEXTURE ? 2 : (SHADER == HANA_SHADER_TEXTURE_LIGHT ? 5 : 8));
-    constexpr int NQ = (3 * NA + 3) / 4;
+    constexpr int NA = ShaderAttrs<SHADER>::NA;
+    constexpr int NQ = ShaderAttrs<SHADER>::NQ;
     __shared__ RasterSmem sm;
     const PassParams& p = q.p;
     const int tid = threadIdx.x;
@@ -429,6 +454,8 @@ __global__ void __launch_bounds__(RASTER_THREADS)
     const bool tma = q.use_tma != 0;
 
     if (p.counters->pool_used > p.pool_cap) return; /* lists are incomplete: host re-runs with a larger pool */
+    const uint32_t n_work = p.counters->n_work;
+    const uint32_t n_slots = (uint32_t)p.n_frames * (uint32_t)p.n_tiles;
 
     /* constant clear tiles */
     if (MODE != MODE_RMW) {
@@ -436,8 +463,14 @@ __global__ void __launch_bounds__(RASTER_THREADS)
         sm.clr_depth[tid] = q.clear_depth;
         sm.clr_r8[tid] = 0;
     }
+    /* Work queue, software-pipelined on thread 0: the atomic for item k+2 and the entry load for item k+1
+     * are issued while item k is processed and consumed only at the end of it, so neither latency is exposed. */
+    uint32_t next_idx = 0;
+    uint4 next_entry = make_uint4(WORK_INVALID, 0u, 0u, 0u);
     if (tid == 0) {
-        sm.item = atomicAdd(&p.counters->work_cursor, 1u);
+        const uint32_t i0 = atomicAdd(&p.counters->work_cursor, 2u);
+        sm.cur = fetch_work(p, i0, n_work);
+        next_entry = fetch_work(p, i0 + 1u, n_work);
         if (MODE == MODE_RMW) {
             mbar_init(&sm.bar, 1);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -446,31 +479,25 @@ __global__ void __launch_bounds__(RASTER_THREADS)
     fence_async_smem();
     __syncthreads();
 
-    const uint32_t n_work = p.counters->n_work;
-    const uint32_t n_slots = (uint32_t)p.n_frames * (uint32_t)p.n_tiles;
     bool clear_done = (MODE == MODE_RMW); /* per warp */
     uint32_t load_phase = 0;
     uint32_t covered_acc = 0;
 
     while (true) {
-        const uint32_t it = sm.item;
-        __syncthreads();
-        if (it >= n_work) break; /* uniform: every thread read the same item */
-        if (tid == 0) sm.item = atomicAdd(&p.counters->work_cursor, 1u); /* prefetch; published by the syncs below */
+        const uint4 cur = sm.cur;
+        if (cur.x == WORK_INVALID) break; /* uniform: every thread read the same entry */
+        if (tid == 0) next_idx = atomicAdd(&p.counters->work_cursor, 1u); /* consumed at the end of this tile */
 
         /* clear duty while raster work remains: warp 1 claims 32 (frame,tile) slots per tile it helps rasterise */
         if (MODE != MODE_RMW && wid == 1 && !clear_done) clear_done = clear_slots<MODE>(q, sm, tm_color, tm_depth, tm_r8, n_slots);
 
         /* -- one non-empty tile -- */
-        const uint32_t item = p.work[it];
-        const int f = (int)(item >> TILE_BITS);
-        const int t = (int)(item & TILE_MASK);
-        const int tx = t % p.tiles_x, ty = t / p.tiles_x;
+        const int f = (int)(cur.x >> TILE_BITS);
+        const int tx = (int)(cur.x & 1023u), ty = (int)((cur.x >> 10) & 1023u);
         const int px = tx * TILE + lx, py = ty * TILE + ly;
         const bool in_frame = px < p.W && py < p.H;
-        const uint32_t cnt = p.tile_count[(size_t)f * p.n_tiles + t];
-        const uint32_t off = p.tile_offset[(size_t)f * p.n_tiles + t];
-        const TriRecord* recs = p.tri_rec + (size_t)f * p.tri_cap;
+        const uint32_t cnt = cur.y;
+        const float4* list = p.tile_recs + (size_t)cur.z * 4;
 
         float bz = q.clear_depth;
         uint32_t bcol = q.clear_color;
@@ -496,42 +523,58 @@ __global__ void __launch_bounds__(RASTER_THREADS)
         uint32_t bidx = 0;
         float bw0 = 0.f, bw1 = 0.f, bw2 = 0.f;
         const float fpx = (float)px, fpy = (float)py;
+        /* this warp's 8x4 block in pixels, packed like the records' ranges */
+        const int bx0 = tx * TILE + wbx, by0 = ty * TILE + wby;
 
         for (uint32_t c0 = 0; c0 < cnt; c0 += CHUNK) {
             const int n = (int)min((uint32_t)CHUNK, cnt - c0);
-            __syncthreads(); /* previous chunk fully consumed */
+            if (c0) __syncthreads(); /* previous chunk fully consumed (the first chunk follows the end-of-tile barrier) */
             if (tid < n * 4) {
-                uint32_t ti = p.refs[off + c0 + (tid >> 2)];
-                sm.tri[tid] = __ldg(reinterpret_cast<const float4*>(recs + ti) + (tid & 3));
-                if ((tid & 3) == 0) sm.tri_idx[tid >> 2] = ti;
+                const float4 v = __ldg(list + (size_t)c0 * 4 + tid);
+                sm.tri[tid] = v;
+                if ((tid & 3) == 2) {
+                    sm.bbx[tid >> 2] = __float_as_uint(v.x);
+                    sm.bby[tid >> 2] = __float_as_uint(v.y);
+                }
             }
             __syncthreads();
-            for (int j = 0; j < n; j++) {
-                const float4 r1 = sm.tri[j * 4 + 1];
-                const float4 r2 = sm.tri[j * 4 + 2];
-                const uint32_t bbx = __float_as_uint(r1.w), bby = __float_as_uint(r2.x);
-                const int x0 = (int)(bbx & 0xFFFFu), x1 = (int)(bbx >> 16);
-                const int y0 = (int)(bby & 0xFFFFu), y1 = (int)(bby >> 16);
-                /* warp-uniform reject of the 8x4 block against the triangle's pixel range */
-                const int bx = tx * TILE + wbx, by = ty * TILE + wby;
-                if (x1 < bx || x0 > bx + 7 || y1 < by || y0 > by + 3) continue;
-                const float4 r0 = sm.tri[j * 4 + 0];
-                float ux, uy;
-                bool cov = coverage_test(r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, fpx, fpy, ux, uy);
-                cov = cov && px >= x0 && px <= x1 && py >= y0 && py <= y1;
-                if (cov) {
-                    float w0, w1, w2;
-                    barycentric_weights(ux, uy, r1.z, w0, w1, w2);
-                    float z = interpolate_depth(r2.y, r2.z, r2.w, w0, w1, w2);
-                    int key = (int)__float_as_uint(sm.tri[j * 4 + 3].w);
-                    bool win = (bkey < 0) ? !(z > bz) : (z < bz || (z == bz && key > bkey));
-                    if (win) {
-                        bz = z;
-                        bkey = key;
-                        bidx = sm.tri_idx[j];
-                        bw0 = w0;
-                        bw1 = w1;
-                        bw2 = w2;
+            /* per-warp compaction: which staged triangles' pixel ranges meet this warp's block */
+#pragma unroll
+            for (int half = 0; half < CHUNK / 32; half++) {
+                const int jj = half * 32 + (int)lane;
+                bool hit = false;
+                if (jj < n) {
+                    const uint32_t bbx = sm.bbx[jj], bby = sm.bby[jj];
+                    hit = !((int)(bbx >> 16) < bx0 || (int)(bbx & 0xFFFFu) > bx0 + 7 || (int)(bby >> 16) < by0 ||
+                            (int)(bby & 0xFFFFu) > by0 + 3);
+                }
+                unsigned m = __ballot_sync(0xFFFFFFFFu, hit);
+                while (m) {
+                    const int j = half * 32 + (__ffs((int)m) - 1);
+                    m &= m - 1u;
+                    const float4 r0 = sm.tri[j * 4 + 0];
+                    const float4 r1 = sm.tri[j * 4 + 1];
+                    const float4 r2 = sm.tri[j * 4 + 2];
+                    const float4 r3 = sm.tri[j * 4 + 3];
+                    const uint32_t bbx = __float_as_uint(r2.x), bby = __float_as_uint(r2.y);
+                    float ux, uy, su;
+                    bool cov = coverage_test(r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r3.w, fpx, fpy, ux, uy, su);
+                    cov = cov && px >= (int)(bbx & 0xFFFFu) && px <= (int)(bbx >> 16) && py >= (int)(bby & 0xFFFFu) &&
+                          py <= (int)(bby >> 16);
+                    if (cov) {
+                        float w0, w1, w2;
+                        barycentric_weights(ux, uy, su, r1.z, r1.w, w0, w1, w2);
+                        const float z = interpolate_depth(r3.x, r3.y, r3.z, w0, w1, w2);
+                        const int key = (int)__float_as_uint(r2.w);
+                        const bool win = (bkey < 0) ? !(z > bz) : (z < bz || (z == bz && key > bkey));
+                        if (win) {
+                            bz = z;
+                            bkey = key;
+                            bidx = __float_as_uint(r2.z);
+                            bw0 = w0;
+                            bw1 = w1;
+                            bw2 = w2;
+                        }
                     }
                 }
             }
@@ -539,13 +582,13 @@ __global__ void __launch_bounds__(RASTER_THREADS)
 
         /* -- shade the winner (graphics.cpp:362-373) -- */
         if (bkey >= 0) {
-            const float4 r3 = __ldg(reinterpret_cast<const float4*>(recs + bidx) + 3);
-            VaryingWeights vw = varying_weights(bw0, bw1, bw2, r3.x, r3.y, r3.z);
             const float4* ap = p.tri_attr + ((size_t)f * p.tri_cap + bidx) * NQ;
-            float a[NQ * 4];
+            const float4 rw = __ldg(ap);
+            VaryingWeights vw = varying_weights(bw0, bw1, bw2, rw.x, rw.y, rw.z);
+            float a[(NQ - 1) * 4];
 #pragma unroll
-            for (int k = 0; k < NQ; k++) {
-                float4 v = __ldg(ap + k);
+            for (int k = 0; k < NQ - 1; k++) {
+                float4 v = __ldg(ap + 1 + k);
                 a[4 * k] = v.x;
                 a[4 * k + 1] = v.y;
                 a[4 * k + 2] = v.z;
@@ -576,16 +619,6 @@ __global__ void __launch_bounds__(RASTER_THREADS)
                 sm.out_depth[ly * TILE + lx] = bz;
             }
             fence_async_smem();
-            __syncthreads();
-            if (tid == 0) {
-                if (MODE == MODE_SHADOW_R8) {
-                    tma_store_3d(&tm_r8, sm.out_r8, tx * TILE, ty * TILE, f);
-                } else {
-                    tma_store_3d(&tm_color, sm.out_color, tx * TILE, ty * TILE, f);
-                    tma_store_3d(&tm_depth, sm.out_depth, tx * TILE, ty * TILE, f);
-                }
-                tma_commit();
-            }
         } else if (in_frame) {
             if (MODE == MODE_SHADOW_R8) {
                 q.shadow_out[(size_t)f * q.shadow_out_frame_stride + (size_t)py * q.shadow_out_pitch + px] =
@@ -599,6 +632,21 @@ __global__ void __launch_bounds__(RASTER_THREADS)
         if (q.pixels_covered && lane == 0 && covered_acc) {
             atomicAdd(q.pixels_covered + f, covered_acc);
             covered_acc = 0;
+        }
+        /* advance the queue: publish the prefetched entry, start the load of the one after it */
+        if (tid == 0) {
+            sm.cur = next_entry;
+            next_entry = fetch_work(p, next_idx, n_work);
+        }
+        __syncthreads(); /* end of tile: staging tile complete, sm.cur published, sm.tri free */
+        if (tma && tid == 0) {
+            if (MODE == MODE_SHADOW_R8) {
+                tma_store_3d(&tm_r8, sm.out_r8, tx * TILE, ty * TILE, f);
+            } else {
+                tma_store_3d(&tm_color, sm.out_color, tx * TILE, ty * TILE, f);
+                tma_store_3d(&tm_depth, sm.out_depth, tx * TILE, ty * TILE, f);
+            }
+            tma_commit();
         }
     }
     /* raster queue drained: every warp helps with what is left of the clear queue */

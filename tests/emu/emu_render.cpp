@@ -43,9 +43,10 @@ int emu_coverage(const float* abc6, int W, int H, int px, int py, float* w3) {
     float s1x = abc6[5] - abc6[1], s1y = abc6[3] - abc6[1];
     float uz = s0x * s1y - s0y * s1x;
     if (!(fabsf(uz) > 0.01f)) return 0;
-    float ux, uy;
-    bool in = coverage_test(abc6[0], abc6[1], s0x, s0y, s1x, s1y, uz, (float)px, (float)py, ux, uy);
-    barycentric_weights(ux, uy, uz, w3[0], w3[1], w3[2]);
+    float ux, uy, s;
+    bool in = coverage_test(abc6[0], abc6[1], s0x, s0y, s1x, s1y, uz, fabsf(uz) * 5.9604644775390625e-08f, (float)px, (float)py,
+                            ux, uy, s);
+    barycentric_weights(ux, uy, s, uz, 1.f / uz, w3[0], w3[1], w3[2]);
     return in ? 1 : 0;
 }
 
@@ -91,10 +92,10 @@ void emu_draw(int shader, const HanaUniforms* hu, const float* a2v, int ncorners
         int x0 = r.bbx & 0xFFFF, x1 = r.bbx >> 16, y0 = r.bby & 0xFFFF, y1 = r.bby >> 16;
         for (int py = y0; py <= y1; py++)
             for (int px = x0; px <= x1; px++) {
-                float ux, uy;
-                if (!coverage_test(r.ax, r.ay, r.s0x, r.s0y, r.s1x, r.s1y, r.uz, (float)px, (float)py, ux, uy)) continue;
+                float ux, uy, s;
+                if (!coverage_test(r.ax, r.ay, r.s0x, r.s0y, r.s1x, r.s1y, r.uz, r.thr, (float)px, (float)py, ux, uy, s)) continue;
                 float w0, w1, w2;
-                barycentric_weights(ux, uy, r.uz, w0, w1, w2);
+                barycentric_weights(ux, uy, s, r.uz, r.ruz, w0, w1, w2);
                 float z = interpolate_depth(r.d0, r.d1, r.d2, w0, w1, w2);
                 size_t i = (size_t)py * W + px;
                 int key = (int)r.key;
