@@ -1,5 +1,3 @@
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -x -q -m gpu 2>&1 | tail -8
-timeout 600 python bench.py --no-cpu-baseline > gpurun_out/bench.json 2> gpurun_out/bench.err; echo bench rc=$?
-tail -3 gpurun_out/bench.err
+timeout 1500 python -m pytest tests -x -q -m gpu --durations=8 2>&1 | tail -25

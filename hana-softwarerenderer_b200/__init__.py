@@ -31,7 +31,7 @@ from .api import (  # noqa: F401
     lib_path,
     load,
 )
-from . import scene  # noqa: F401
+from . import scene, sharding  # noqa: F401
 from .scene import (  # noqa: F401
     OrbitCamera,
     Scene,

@@ -372,6 +372,23 @@ extern "C" int hana_model_upload(hana_ctx* ctx, const float* a2v, int ncorners, 
     *out = m;
     return HANA_OK;
 }
+extern "C" int hana_model_update(hana_model* m, const float* a2v, int ncorners) {
+    if (!m || (!a2v && ncorners > 0)) return fail(HANA_E_INVALID, "NULL argument");
+    if (ncorners != m->ncorners) return fail(HANA_E_INVALID, "corner count differs from the uploaded model");
+    if (ncorners == 0) return HANA_OK;
+    hana_ctx* ctx = m->ctx;
+    HANA_TRY(use_device(ctx));
+    std::vector<float4> posu(ncorners), nrmv(ncorners);
+    for (int i = 0; i < ncorners; i++) {
+        const float* a = a2v + (size_t)i * 8;
+        posu[i] = make_float4(a[0], a[1], a[2], a[6]);
+        nrmv[i] = make_float4(a[3], a[4], a[5], a[7]);
+    }
+    CU_TRY(cudaMemcpyAsync(m->posu, posu.data(), (size_t)ncorners * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
+    CU_TRY(cudaMemcpyAsync(m->nrmv, nrmv.data(), (size_t)ncorners * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
+    CU_TRY(cudaStreamSynchronize(ctx->stream));
+    return HANA_OK;
+}
 extern "C" int hana_model_destroy(hana_model* m) {
     if (!m) return HANA_OK;
     cudaSetDevice(m->ctx->device);
@@ -623,7 +640,7 @@ static int run_pass(hana_ctx* ctx, const PassDesc& d) {
         HANA_TRY(grow(&sc.tri_count, &sc.frames_cap, (size_t)d.n_frames, ctx));
         HANA_TRY(grow(&sc.tile_arrays, &sc.tile_arr_cap, tiles_total * 3, ctx));
         HANA_TRY(grow(&sc.work, &sc.work_cap, tiles_total, ctx));
-        if (!sc.tile_recs) HANA_TRY(grow(&sc.tile_recs, &sc.pool_cap, std::max<size_t>(tri_total * 8, 65536) * 4, ctx));
+        if (!sc.tile_recs) HANA_TRY(grow(&sc.tile_recs, &sc.pool_cap, std::max<size_t>(tri_total * 2, 65536) * 4, ctx));
 
         p.posu = d.model->posu;
         p.nrmv = d.model->nrmv;

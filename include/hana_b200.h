@@ -139,6 +139,10 @@ HANA_API int hana_ctx_profile_get(hana_ctx* ctx, int kind, double* total_ms, uin
  * {obj_pos.xyz, obj_normal.xyz, uv.xy}, 3 consecutive corners per face in the
  * order graphics.cpp:380-386 visits them. ncorners must be a multiple of 3. */
 HANA_API int hana_model_upload(hana_ctx* ctx, const float* a2v, int ncorners, hana_model** out);
+/* Replace the stream of an uploaded model in place (same corner count): the reference's
+ * Model::normal() re-normalises its normals on every access (model.cpp:108-111), so a faithful
+ * caller re-gathers the stream per pass. */
+HANA_API int hana_model_update(hana_model* m, const float* a2v, int ncorners);
 HANA_API int hana_model_destroy(hana_model* m);
 HANA_API int hana_model_ncorners(const hana_model* m);
 

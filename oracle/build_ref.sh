@@ -46,4 +46,13 @@ COMMON="$TMP/vector.o $TMP/color.o $TMP/maths.o $TMP/model.o $TMP/IShader.o $TMP
 # the plain build still needs the hook symbols referenced by nothing -> none needed
 $CXX -shared -o "$OUT/libhana_ref.so" $COMMON "$TMP/graphics_plain.o" "$TMP/driver_plain.o" -Wl,--allow-multiple-definition -Wl,-Bsymbolic
 $CXX -shared -o "$OUT/libhana_ref_inst.so" $COMMON "$TMP/graphics_inst.o" "$TMP/driver_inst.o" -Wl,--allow-multiple-definition -Wl,-Bsymbolic
+# The drop-in test build: the reference's scene code + this repo's graphics_draw_triangle shim INSTEAD of
+# graphics.cpp, linked against libhana_b200.so (needs a GPU to run; only built when the library exists).
+PKG="$HERE/../hana-softwarerenderer_b200"
+if [ -f "$PKG/libhana_b200.so" ]; then
+  $CXX $F -c "$PKG/host/graphics_dropin.cpp" -o "$TMP/graphics_dropin.o"
+  $CXX -shared -o "$OUT/libhana_ref_dropin.so" $COMMON "$TMP/graphics_dropin.o" "$TMP/driver_plain.o" \
+      -Wl,--allow-multiple-definition -Wl,-Bsymbolic -L"$PKG" -lhana_b200 -Wl,-rpath,'$ORIGIN/../../hana-softwarerenderer_b200'
+  echo "built $OUT/libhana_ref_dropin.so"
+fi
 echo "built $OUT/libhana_ref.so $OUT/libhana_ref_inst.so"

@@ -20,6 +20,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 PORT_SO = os.path.join(HERE, "_build", "libhana_oracle.so")
 REF_SO = os.path.join(HERE, "_ref", "libhana_ref.so")
 REF_INST_SO = os.path.join(HERE, "_ref", "libhana_ref_inst.so")
+# the reference's scene code linked with THIS repo's graphics_draw_triangle shim instead of graphics.cpp
+# (hana-softwarerenderer_b200/host/graphics_dropin.cpp): the object under test of the drop-in parity test
+REF_DROPIN_SO = os.path.join(HERE, "_ref", "libhana_ref_dropin.so")
 ASSET_DIR = os.path.join(HERE, "_ref", "assets")
 
 SHADOW, BLINN, NORMALMAP, GROUND, TOON, TEXTURE, TEXTURE_LIGHT = range(7)
@@ -190,8 +193,10 @@ def reference_available(instrumented=True):
 class Reference:
     """The real reference behind oracle/ref_driver.cpp (one scene per instance)."""
 
-    def __init__(self, obj_path, W, H, shader, instrumented=True):
-        so = REF_INST_SO if instrumented else REF_SO
+    def __init__(self, obj_path, W, H, shader, instrumented=True, dropin=False):
+        if dropin:
+            instrumented = False
+        so = REF_DROPIN_SO if dropin else (REF_INST_SO if instrumented else REF_SO)
         if not os.path.exists(so):
             raise FileNotFoundError(so + " (run oracle/build_ref.sh where /root/reference exists)")
         self.inst = instrumented

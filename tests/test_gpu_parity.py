@@ -197,3 +197,35 @@ def test_empty_model_and_errors(hana, ctx):
         ctx.draw(rb, m, 99, u)
     rb.close()
     m.close()
+
+
+def test_dropin_graphics_draw_triangle(hana, horacle):
+    """The reference's OWN scene code (Scene/Camera/DrawModel::draw, compiled from its unmodified sources) linked with
+    this repo's graphics_draw_triangle(DrawData*) instead of graphics.cpp, against the plain reference build:
+    same OBJ/TGA files, same camera motion, frame by frame."""
+    import os
+    from conftest import ASSET_DIR
+    H = horacle
+    obj = os.path.join(ASSET_DIR, "diablo3_pose", "diablo3_pose.obj")
+    if not (os.path.exists(H.REF_DROPIN_SO) and os.path.exists(H.REF_SO) and os.path.exists(obj)):
+        pytest.skip("oracle/_ref drop-in build missing (needs /root/reference at build time)")
+    W, Hh = 640, 480
+    for shader in (H.NORMALMAP, H.BLINN, H.TOON):
+        ref = H.Reference(obj, W, Hh, shader, instrumented=False)
+        gpu = H.Reference(obj, W, Hh, shader, dropin=True)
+        for step in range(3):
+            for r in (ref, gpu):
+                r.camera_motion(orbit=(0.11, 0.03), dolly=0.5)
+            _, c0, d0 = ref.render(True)
+            _, c1, d1 = gpu.render(True)
+            assert ref.uniforms().to_bytes() == gpu.uniforms().to_bytes()
+            check(compare_frames(c1, d1, c0, d0), W * Hh)
+        # shadows off + the reference's very first-frame state (depth 1.0, alpha 255: renderbuffer.cpp:6-7)
+        ref2 = H.Reference(obj, W, Hh, shader, instrumented=False)
+        gpu2 = H.Reference(obj, W, Hh, shader, dropin=True)
+        _, c0, d0 = ref2.render(False, clear=False)
+        _, c1, d1 = gpu2.render(False, clear=False)
+        assert np.array_equal(d0.view(np.uint32), d1.view(np.uint32))
+        assert np.abs(c0.astype(int) - c1.astype(int)).max() <= 1 and np.array_equal(c0[..., 3], c1[..., 3])
+        for r in (ref, gpu, ref2, gpu2):
+            r.close()
