@@ -580,7 +580,7 @@ template <int MODE>
 static int launch_raster(hana_ctx* ctx, int shader, int blocks, const RasterParams& rp, const CUtensorMap& a,
                          const CUtensorMap& b, const CUtensorMap& c) {
 #define HANA_RASTER_CASE(S) \
-    case S: raster_kernel<S, MODE><<<blocks, RASTER_THREADS, 0, ctx->stream>>>(rp, a, b, c); break;
+    case S: raster_kernel<S, MODE><<<blocks, RW_THREADS, 0, ctx->stream>>>(rp, a, b, c); break;
     switch (shader) {
         HANA_RASTER_CASE(HANA_SHADER_SHADOW)
         HANA_RASTER_CASE(HANA_SHADER_BLINN)
@@ -599,7 +599,7 @@ template <int MODE>
 static int raster_occupancy(int shader) {
     int occ = 0;
 #define HANA_OCC_CASE(S) \
-    case S: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, raster_kernel<S, MODE>, RASTER_THREADS, 0); break;
+    case S: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, raster_kernel<S, MODE>, RW_THREADS, 0); break;
     switch (shader) {
         HANA_OCC_CASE(HANA_SHADER_SHADOW)
         HANA_OCC_CASE(HANA_SHADER_BLINN)
@@ -761,8 +761,8 @@ static int run_pass(hana_ctx* ctx, const PassDesc& d) {
         cudaGetLastError();
         if (occ <= 0) occ = 1;
     }
-    size_t want = cnt.n_work;
-    if (d.mode != MODE_RMW) want = std::max<size_t>(want, (tiles_total + 255) / 256);
+    size_t want = ((size_t)cnt.n_work + RW_WARPS - 1) / RW_WARPS; /* one tile per warp at a time */
+    if (d.mode != MODE_RMW) want = std::max<size_t>(want, (tiles_total + 1023) / 1024);
     int blocks = (int)std::max<size_t>(1, std::min<size_t>(want, (size_t)ctx->sm_count * occ));
     static const CUtensorMap dummy = {};
     const CUtensorMap& ta = d.tm_color ? *d.tm_color : dummy;

@@ -32,8 +32,6 @@ namespace hana {
 
 constexpr int TILE = 16;             /* screen tile edge (pixels) */
 constexpr int TILE_PIX = TILE * TILE;
-constexpr int RASTER_THREADS = 256;  /* one thread per tile pixel */
-constexpr int CHUNK = 64;            /* triangles staged in shared memory per round */
 constexpr int TILE_BITS = 20;        /* work item = frame << 20 | tile_y << 10 | tile_x */
 constexpr uint32_t TILE_MASK = (1u << TILE_BITS) - 1u;
 constexpr uint32_t WORK_INVALID = 0xFFFFFFFFu;
@@ -168,8 +166,8 @@ struct ShaderAttrs {
 constexpr int MAX_ATTR_QUADS = 7;
 
 /* Raster record in memory, 4 x float4:
- *   q0 = ax, ay, s0x, s0y      q1 = s1x, s1y, uz, 1/uz
- *   q2 = bbx, bby, triangle index (attribute block), order key      q3 = d0, d1, d2, |uz| * 2^-24 */
+ *   q0 = ax, ay, s0x, s0y      q1 = s1x, s1y, uz, |uz| * 2^-24      (all the coverage test reads)
+ *   q2 = bbx, bby, triangle index (attribute block), order key      q3 = d0, d1, d2, 1/uz   (covered pixels only) */
 template <int SHADER>
 __device__ __forceinline__ void store_triangle(const PassParams& p, int f, uint32_t slot, const TriRecord& r,
                                                const float* v0, const float* v1, const float* v2) {
@@ -177,9 +175,9 @@ __device__ __forceinline__ void store_triangle(const PassParams& p, int f, uint3
     constexpr int NQ = ShaderAttrs<SHADER>::NQ;
     float4* dst = p.tri_rec + ((size_t)f * p.tri_cap + slot) * 4;
     dst[0] = make_float4(r.ax, r.ay, r.s0x, r.s0y);
-    dst[1] = make_float4(r.s1x, r.s1y, r.uz, r.ruz);
+    dst[1] = make_float4(r.s1x, r.s1y, r.uz, r.thr);
     dst[2] = make_float4(__uint_as_float(r.bbx), __uint_as_float(r.bby), __uint_as_float(slot), __uint_as_float(r.key));
-    dst[3] = make_float4(r.d0, r.d1, r.d2, r.thr);
+    dst[3] = make_float4(r.d0, r.d1, r.d2, r.ruz);
     float a[(NQ - 1) * 4];
 #pragma unroll
     for (int k = 0; k < NA; k++) {
@@ -372,34 +370,48 @@ __global__ void __launch_bounds__(256) fill_kernel(PassParams p) {
         }
 }
 
-/* ---- raster ------------------------------------------------------------------ */
-struct alignas(128) RasterSmem {
-    uint32_t out_color[TILE_PIX]; /* 1 KB, TMA box 16x16 u32 */
-    float out_depth[TILE_PIX];
-    uint32_t clr_color[TILE_PIX]; /* constant clear tiles, TMA store source for empty tiles */
-    float clr_depth[TILE_PIX];
-    float4 tri[CHUNK * 4];        /* staged raster records */
-    uint32_t bbx[CHUNK];          /* their pixel ranges, conflict-free for the per-warp overlap test */
-    uint32_t bby[CHUNK];
-    alignas(128) uint8_t out_r8[TILE_PIX]; /* MODE_SHADOW_R8 tile, box 16x16 u8 */
-    alignas(128) uint8_t clr_r8[TILE_PIX];
-    alignas(16) uint4 cur;        /* the work entry being processed: {item, count, offset, -} */
+/* ---- raster ------------------------------------------------------------------
+ * One WARP per 16x16 tile, no CTA-wide barrier anywhere in the tile loop (v2 spent a third of its
+ * time at __syncthreads waiting for the slowest of 8 warps). A lane owns 8 pixels of the tile: pixel
+ * (lane & 7, lane >> 3) of each of the eight 8x4 sub-blocks (2 across, 4 down). The tile's records
+ * are staged 32 at a time in the warp's private shared memory; lane j also computes which sub-blocks
+ * record j's pixel range meets, so the triangle loop is warp-uniform and skips sub-blocks without a
+ * single per-pixel instruction. The (min depth, max key) resolve lives in registers as
+ * {depth, list ordinal} per pixel; after the last record the state is parked in shared memory and
+ * the winners are shaded one sub-block at a time (weights recomputed from the winning record, which
+ * costs less than carrying three weights per pixel through the resolve loop). The warp's tile is
+ * flushed with TMA stores issued by lane 0; warps never wait for each other. */
+constexpr int RW_WARPS = 4;
+constexpr int RW_THREADS = RW_WARPS * 32;
+constexpr int RW_CHUNK = 32;
+constexpr uint32_t ORD_NONE = 0xFFFFFFFFu;
+
+template <int MODE>
+struct alignas(128) WarpTile {
+    /* TMA sources/destinations first: each 128-byte aligned */
+    uint32_t color[MODE == MODE_SHADOW_R8 ? 32 : TILE_PIX]; /* box 16x16 u32 */
+    float depth[MODE == MODE_SHADOW_R8 ? 32 : TILE_PIX];
+    uint8_t r8[MODE == MODE_SHADOW_R8 ? TILE_PIX : 128];    /* box 16x16 u8 */
+    uint32_t ord[TILE_PIX];                                 /* winning list ordinal per pixel, parked for shading */
+    float4 tri[RW_CHUNK * 4];                               /* staged raster records */
     alignas(8) uint64_t bar;
 };
-
-/* One warp claims 32 consecutive (frame,tile) slots and clears those no triangle touches:
- * by TMA, two fire-and-forget bulk stores per lane from the constant tiles. Returns true
- * when the queue is exhausted. */
 template <int MODE>
-__device__ __forceinline__ bool clear_slots(const RasterParams& q, RasterSmem& sm, const CUtensorMap& tm_color,
-                                            const CUtensorMap& tm_depth, const CUtensorMap& tm_r8, uint32_t n_slots) {
+struct alignas(128) RasterSmem {
+    WarpTile<MODE> w[RW_WARPS];
+    uint32_t clr_color[TILE_PIX]; /* constant clear tiles, TMA store source for empty tiles */
+    float clr_depth[TILE_PIX];
+    alignas(128) uint8_t clr_r8[TILE_PIX];
+};
+
+/* The 32 (frame,tile) slots [base, base+32): those no triangle touches are cleared by TMA, two
+ * fire-and-forget bulk stores per lane from the constant tiles. */
+template <int MODE>
+__device__ __forceinline__ void clear_slots(const RasterParams& q, RasterSmem<MODE>& sm, const CUtensorMap& tm_color,
+                                            const CUtensorMap& tm_depth, const CUtensorMap& tm_r8, uint32_t base,
+                                            uint32_t n_slots) {
     const PassParams& p = q.p;
-    const unsigned lane = threadIdx.x & 31u;
-    uint32_t base = 0;
-    if (lane == 0) base = atomicAdd(&p.counters->clear_cursor, 32u);
-    base = __shfl_sync(0xFFFFFFFFu, base, 0);
-    if (base >= n_slots) return true;
-    const uint32_t s = base + lane;
+    const uint32_t s = base + (threadIdx.x & 31u);
     if (s < n_slots && p.tile_count[s] == 0u) {
         const int f = (int)(s / (uint32_t)p.n_tiles), t = (int)(s % (uint32_t)p.n_tiles);
         const int tx = t % p.tiles_x, ty = t / p.tiles_x;
@@ -429,7 +441,6 @@ __device__ __forceinline__ bool clear_slots(const RasterParams& q, RasterSmem& s
             }
         }
     }
-    return false;
 }
 
 __device__ __forceinline__ uint4 fetch_work(const PassParams& p, uint32_t idx, uint32_t n_work) {
@@ -437,221 +448,272 @@ __device__ __forceinline__ uint4 fetch_work(const PassParams& p, uint32_t idx, u
     return make_uint4(WORK_INVALID, 0u, 0u, 0u);
 }
 
+/* Sub-blocks (bit r*2+c: column half c, row quarter r) of the tile at (X0,Y0) that the pixel range meets.
+ * The range is known to meet the tile (that is why the record is in this tile's list). */
+__device__ __forceinline__ uint32_t subblock_mask(uint32_t bbx, uint32_t bby, int X0, int Y0) {
+    const int cx0 = max((int)(bbx & 0xFFFFu) - X0, 0) >> 3, cx1 = min((int)(bbx >> 16) - X0, TILE - 1) >> 3;
+    const int ry0 = max((int)(bby & 0xFFFFu) - Y0, 0) >> 2, ry1 = min((int)(bby >> 16) - Y0, TILE - 1) >> 2;
+    const uint32_t cm = (2u << cx1) - (1u << cx0);        /* 2 bits */
+    const uint32_t rm = (2u << ry1) - (1u << ry0);        /* 4 bits */
+    const uint32_t spread = (rm & 1u) | ((rm & 2u) << 1) | ((rm & 4u) << 2) | ((rm & 8u) << 3);
+    return cm * spread;
+}
+
 template <int SHADER, int MODE>
-__global__ void __launch_bounds__(RASTER_THREADS)
+__global__ void __launch_bounds__(RW_THREADS)
     raster_kernel(RasterParams q, const __grid_constant__ CUtensorMap tm_color, const __grid_constant__ CUtensorMap tm_depth,
                   const __grid_constant__ CUtensorMap tm_r8) {
     constexpr int NA = ShaderAttrs<SHADER>::NA;
     constexpr int NQ = ShaderAttrs<SHADER>::NQ;
-    __shared__ RasterSmem sm;
+    constexpr unsigned FULL = 0xFFFFFFFFu;
+    __shared__ RasterSmem<MODE> sm;
     const PassParams& p = q.p;
-    const int tid = threadIdx.x;
-    const unsigned lane = tid & 31u, wid = tid >> 5;
-    /* warp w owns an 8x4 pixel block of the tile: 2 blocks across, 4 down */
-    const int lx = (int)(wid & 1u) * 8 + (int)(lane & 7u);
-    const int ly = (int)(wid >> 1) * 4 + (int)(lane >> 3);
-    const int wbx = (int)(wid & 1u) * 8, wby = (int)(wid >> 1) * 4;
+    const unsigned lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
+    WarpTile<MODE>& wt = sm.w[wid];
+    const int lx = (int)(lane & 7u), ly = (int)(lane >> 3);
     const bool tma = q.use_tma != 0;
 
     if (p.counters->pool_used > p.pool_cap) return; /* lists are incomplete: host re-runs with a larger pool */
     const uint32_t n_work = p.counters->n_work;
     const uint32_t n_slots = (uint32_t)p.n_frames * (uint32_t)p.n_tiles;
 
-    /* constant clear tiles */
     if (MODE != MODE_RMW) {
-        sm.clr_color[tid] = q.clear_color;
-        sm.clr_depth[tid] = q.clear_depth;
-        sm.clr_r8[tid] = 0;
-    }
-    /* Work queue, software-pipelined on thread 0: the atomic for item k+2 and the entry load for item k+1
-     * are issued while item k is processed and consumed only at the end of it, so neither latency is exposed. */
-    uint32_t next_idx = 0;
-    uint4 next_entry = make_uint4(WORK_INVALID, 0u, 0u, 0u);
-    if (tid == 0) {
-        const uint32_t i0 = atomicAdd(&p.counters->work_cursor, 2u);
-        sm.cur = fetch_work(p, i0, n_work);
-        next_entry = fetch_work(p, i0 + 1u, n_work);
-        if (MODE == MODE_RMW) {
-            mbar_init(&sm.bar, 1);
-            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        for (int i = threadIdx.x; i < TILE_PIX; i += RW_THREADS) {
+            sm.clr_color[i] = q.clear_color;
+            sm.clr_depth[i] = q.clear_depth;
+            sm.clr_r8[i] = 0;
         }
+    } else if (lane == 0) {
+        mbar_init(&wt.bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     fence_async_smem();
-    __syncthreads();
+    __syncthreads(); /* the only CTA-wide barrier */
 
-    bool clear_done = (MODE == MODE_RMW); /* per warp */
+    /* Work queue, software-pipelined on lane 0: the atomic for item k+2 and the entry load for item k+1 are in
+     * flight while item k is processed and are consumed only at the end of it, so neither latency is exposed. */
+    uint32_t i_next = 0;
+    uint4 e_cur = make_uint4(WORK_INVALID, 0u, 0u, 0u);
+    if (lane == 0) {
+        const uint32_t i0 = atomicAdd(&p.counters->work_cursor, 2u);
+        e_cur = fetch_work(p, i0, n_work);
+        i_next = i0 + 1u;
+    }
+    bool clear_done = (MODE == MODE_RMW);
     uint32_t load_phase = 0;
-    uint32_t covered_acc = 0;
 
     while (true) {
-        const uint4 cur = sm.cur;
-        if (cur.x == WORK_INVALID) break; /* uniform: every thread read the same entry */
-        if (tid == 0) next_idx = atomicAdd(&p.counters->work_cursor, 1u); /* consumed at the end of this tile */
-
-        /* clear duty while raster work remains: warp 1 claims 32 (frame,tile) slots per tile it helps rasterise */
-        if (MODE != MODE_RMW && wid == 1 && !clear_done) clear_done = clear_slots<MODE>(q, sm, tm_color, tm_depth, tm_r8, n_slots);
+        uint4 cur;
+        cur.x = __shfl_sync(FULL, e_cur.x, 0);
+        if (cur.x == WORK_INVALID) break;
+        cur.y = __shfl_sync(FULL, e_cur.y, 0);
+        cur.z = __shfl_sync(FULL, e_cur.z, 0);
+        uint4 e_nxt = make_uint4(WORK_INVALID, 0u, 0u, 0u);
+        uint32_t i_nn = 0, clr_base = 0;
+        if (lane == 0) {
+            e_nxt = fetch_work(p, i_next, n_work);
+            i_nn = atomicAdd(&p.counters->work_cursor, 1u);
+            if (MODE != MODE_RMW && !clear_done) clr_base = atomicAdd(&p.counters->clear_cursor, 32u);
+        }
 
         /* -- one non-empty tile -- */
         const int f = (int)(cur.x >> TILE_BITS);
         const int tx = (int)(cur.x & 1023u), ty = (int)((cur.x >> 10) & 1023u);
-        const int px = tx * TILE + lx, py = ty * TILE + ly;
-        const bool in_frame = px < p.W && py < p.H;
+        const int X0 = tx * TILE, Y0 = ty * TILE;
         const uint32_t cnt = cur.y;
         const float4* list = p.tile_recs + (size_t)cur.z * 4;
+        const float fpx0 = (float)(X0 + lx), fpx1 = (float)(X0 + 8 + lx);
+        const float fpy0 = (float)(Y0 + ly), fpy1 = (float)(Y0 + 4 + ly), fpy2 = (float)(Y0 + 8 + ly), fpy3 = (float)(Y0 + 12 + ly);
+        const int ipx0 = X0 + lx, ipy0 = Y0 + ly;
 
-        float bz = q.clear_depth;
-        uint32_t bcol = q.clear_color;
+        float bz[8];
+        uint32_t bj[8];
+#pragma unroll
+        for (int sb = 0; sb < 8; sb++) {
+            bz[sb] = q.clear_depth;
+            bj[sb] = ORD_NONE;
+        }
         if (MODE == MODE_RMW) {
             if (tma) {
-                if (tid == 0) {
-                    tma_wait_read0(); /* the previous tile's stores have read out_color/out_depth */
-                    mbar_expect_tx(&sm.bar, 2u * TILE_PIX * 4u);
-                    tma_load_3d(&tm_color, sm.out_color, &sm.bar, tx * TILE, ty * TILE, f);
-                    tma_load_3d(&tm_depth, sm.out_depth, &sm.bar, tx * TILE, ty * TILE, f);
+                if (lane == 0) {
+                    tma_wait_read0(); /* the previous tile's stores have read color/depth */
+                    mbar_expect_tx(&wt.bar, 2u * TILE_PIX * 4u);
+                    tma_load_3d(&tm_color, wt.color, &wt.bar, X0, Y0, f);
+                    tma_load_3d(&tm_depth, wt.depth, &wt.bar, X0, Y0, f);
                 }
-                mbar_wait(&sm.bar, load_phase);
+                mbar_wait(&wt.bar, load_phase);
                 load_phase ^= 1u;
-                bz = sm.out_depth[ly * TILE + lx];
-                bcol = sm.out_color[ly * TILE + lx];
-            } else if (in_frame) {
-                size_t o = (size_t)f * q.frame_stride + (size_t)py * p.W + px;
-                bz = q.depth[o];
-                bcol = q.color[o];
+#pragma unroll
+                for (int sb = 0; sb < 8; sb++) bz[sb] = wt.depth[((sb >> 1) * 4 + ly) * TILE + (sb & 1) * 8 + lx];
+            } else {
+#pragma unroll
+                for (int sb = 0; sb < 8; sb++) {
+                    const int px = ipx0 + (sb & 1) * 8, py = ipy0 + (sb >> 1) * 4;
+                    if (px < p.W && py < p.H) bz[sb] = q.depth[(size_t)f * q.frame_stride + (size_t)py * p.W + px];
+                }
             }
         }
-        int bkey = -1;
-        uint32_t bidx = 0;
-        float bw0 = 0.f, bw1 = 0.f, bw2 = 0.f;
-        const float fpx = (float)px, fpy = (float)py;
-        /* this warp's 8x4 block in pixels, packed like the records' ranges */
-        const int bx0 = tx * TILE + wbx, by0 = ty * TILE + wby;
 
-        for (uint32_t c0 = 0; c0 < cnt; c0 += CHUNK) {
-            const int n = (int)min((uint32_t)CHUNK, cnt - c0);
-            if (c0) __syncthreads(); /* previous chunk fully consumed (the first chunk follows the end-of-tile barrier) */
-            if (tid < n * 4) {
-                const float4 v = __ldg(list + (size_t)c0 * 4 + tid);
-                sm.tri[tid] = v;
-                if ((tid & 3) == 2) {
-                    sm.bbx[tid >> 2] = __float_as_uint(v.x);
-                    sm.bby[tid >> 2] = __float_as_uint(v.y);
-                }
-            }
-            __syncthreads();
-            /* per-warp compaction: which staged triangles' pixel ranges meet this warp's block */
+        for (uint32_t c0 = 0; c0 < cnt; c0 += RW_CHUNK) {
+            const int n = (int)min((uint32_t)RW_CHUNK, cnt - c0);
+            __syncwarp(); /* previous chunk fully consumed */
 #pragma unroll
-            for (int half = 0; half < CHUNK / 32; half++) {
-                const int jj = half * 32 + (int)lane;
-                bool hit = false;
-                if (jj < n) {
-                    const uint32_t bbx = sm.bbx[jj], bby = sm.bby[jj];
-                    hit = !((int)(bbx >> 16) < bx0 || (int)(bbx & 0xFFFFu) > bx0 + 7 || (int)(bby >> 16) < by0 ||
-                            (int)(bby & 0xFFFFu) > by0 + 3);
-                }
-                unsigned m = __ballot_sync(0xFFFFFFFFu, hit);
-                while (m) {
-                    const int j = half * 32 + (__ffs((int)m) - 1);
-                    m &= m - 1u;
-                    const float4 r0 = sm.tri[j * 4 + 0];
-                    const float4 r1 = sm.tri[j * 4 + 1];
-                    const float4 r2 = sm.tri[j * 4 + 2];
-                    const float4 r3 = sm.tri[j * 4 + 3];
-                    const uint32_t bbx = __float_as_uint(r2.x), bby = __float_as_uint(r2.y);
-                    float ux, uy, su;
-                    bool cov = coverage_test(r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r3.w, fpx, fpy, ux, uy, su);
-                    cov = cov && px >= (int)(bbx & 0xFFFFu) && px <= (int)(bbx >> 16) && py >= (int)(bby & 0xFFFFu) &&
-                          py <= (int)(bby >> 16);
-                    if (cov) {
-                        float w0, w1, w2;
-                        barycentric_weights(ux, uy, su, r1.z, r1.w, w0, w1, w2);
-                        const float z = interpolate_depth(r3.x, r3.y, r3.z, w0, w1, w2);
-                        const int key = (int)__float_as_uint(r2.w);
-                        const bool win = (bkey < 0) ? !(z > bz) : (z < bz || (z == bz && key > bkey));
-                        if (win) {
-                            bz = z;
-                            bkey = key;
-                            bidx = __float_as_uint(r2.z);
-                            bw0 = w0;
-                            bw1 = w1;
-                            bw2 = w2;
+            for (int k = 0; k < 4; k++) {
+                const int idx = k * 32 + (int)lane;
+                if (idx < n * 4) wt.tri[idx] = __ldg(list + (size_t)c0 * 4 + idx);
+            }
+            uint32_t mask = 0;
+            if ((int)lane < n) {
+                const float4 b = __ldg(list + ((size_t)c0 + lane) * 4 + 2);
+                mask = subblock_mask(__float_as_uint(b.x), __float_as_uint(b.y), X0, Y0);
+            }
+            __syncwarp();
+            for (int j = 0; j < n; j++) {
+                const uint32_t m = __shfl_sync(FULL, mask, j);
+                const float4 r0 = wt.tri[j * 4 + 0]; /* ax, ay, s0x, s0y */
+                const float4 r1 = wt.tri[j * 4 + 1]; /* s1x, s1y, uz, thr */
+                const float4 r2 = wt.tri[j * 4 + 2]; /* bbx, bby, attr index, key */
+                const uint32_t bbx = __float_as_uint(r2.x), bby = __float_as_uint(r2.y);
+                const int x0 = (int)(bbx & 0xFFFFu), dx = (int)(bbx >> 16) - x0;
+                const int y0 = (int)(bby & 0xFFFFu), dy = (int)(bby >> 16) - y0;
+#pragma unroll
+                for (int sb = 0; sb < 8; sb++) {
+                    if (m & (1u << sb)) { /* warp-uniform */
+                        const float fpx = (sb & 1) ? fpx1 : fpx0;
+                        const float fpy = (sb >> 1) == 0 ? fpy0 : ((sb >> 1) == 1 ? fpy1 : ((sb >> 1) == 2 ? fpy2 : fpy3));
+                        float ux, uy, su;
+                        bool cov = coverage_test(r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w, fpx, fpy, ux, uy, su);
+                        if (cov) {
+                            /* the reference only visits pixels of its clamped bounding box: graphics.cpp:339-351 */
+                            const int px = ipx0 + (sb & 1) * 8, py = ipy0 + (sb >> 1) * 4;
+                            if ((unsigned)(px - x0) <= (unsigned)dx && (unsigned)(py - y0) <= (unsigned)dy) {
+                                const float4 r3 = wt.tri[j * 4 + 3]; /* d0, d1, d2, 1/uz */
+                                float w0, w1, w2;
+                                barycentric_weights(ux, uy, su, r1.z, r3.w, w0, w1, w2);
+                                const float z = interpolate_depth(r3.x, r3.y, r3.z, w0, w1, w2);
+                                bool win;
+                                if (bj[sb] == ORD_NONE) {
+                                    win = !(z > bz[sb]); /* graphics.cpp:359 against the target's depth */
+                                } else {
+                                    win = z < bz[sb];
+                                    if (z == bz[sb]) { /* rare: equal depths, the later submission wins */
+                                        const uint32_t kb = __float_as_uint(__ldg(list + (size_t)bj[sb] * 4 + 2).w);
+                                        win = __float_as_uint(r2.w) > kb;
+                                    }
+                                }
+                                if (win) {
+                                    bz[sb] = z;
+                                    bj[sb] = c0 + (uint32_t)j;
+                                }
+                            }
                         }
                     }
                 }
             }
         }
 
-        /* -- shade the winner (graphics.cpp:362-373) -- */
-        if (bkey >= 0) {
-            const float4* ap = p.tri_attr + ((size_t)f * p.tri_cap + bidx) * NQ;
-            const float4 rw = __ldg(ap);
-            VaryingWeights vw = varying_weights(bw0, bw1, bw2, rw.x, rw.y, rw.z);
-            float a[(NQ - 1) * 4];
-#pragma unroll
-            for (int k = 0; k < NQ - 1; k++) {
-                float4 v = __ldg(ap + 1 + k);
-                a[4 * k] = v.x;
-                a[4 * k + 1] = v.y;
-                a[4 * k + 2] = v.z;
-                a[4 * k + 3] = v.w;
-            }
-            float attr[NA];
-#pragma unroll
-            for (int k = 0; k < NA; k++) attr[k] = interp(vw, a[3 * k], a[3 * k + 1], a[3 * k + 2]);
-            DevShadow sh = q.shadow;
-            if (sh.base) sh.base += (size_t)f * q.shadow_frame_stride;
-            float rgb[3];
-            fragment_shader<SHADER>(p.uniforms[f], attr, q.diffuse, q.normal, sh, rgb);
-            bcol = (bcol & 0xFF000000u) | colour_bytes(rgb); /* alpha is never written: renderbuffer.cpp:38-44 */
-            if (q.primid && f == 0) q.primid[(size_t)py * p.W + px] = (uint32_t)bkey;
+        /* -- park the resolve state, shade the winners one sub-block at a time (graphics.cpp:362-373) -- */
+        if (tma && MODE != MODE_RMW) {
+            if (lane == 0) tma_wait_read0(); /* the previous tile's stores have drained the staging tile */
+            __syncwarp();
         }
-        if (q.pixels_covered) covered_acc += __popc(__ballot_sync(0xFFFFFFFFu, bkey >= 0));
+#pragma unroll
+        for (int sb = 0; sb < 8; sb++) {
+            const int pix = ((sb >> 1) * 4 + ly) * TILE + (sb & 1) * 8 + lx;
+            wt.ord[pix] = bj[sb];
+            if (MODE != MODE_SHADOW_R8) wt.depth[pix] = bz[sb];
+        }
+        uint32_t covered_acc = 0;
+        DevShadow sh = q.shadow;
+        if (sh.base) sh.base += (size_t)f * q.shadow_frame_stride;
+#pragma unroll 1
+        for (int sb = 0; sb < 8; sb++) {
+            const int pix = ((sb >> 1) * 4 + ly) * TILE + (sb & 1) * 8 + lx;
+            const int px = ipx0 + (sb & 1) * 8, py = ipy0 + (sb >> 1) * 4;
+            const bool in_frame = px < p.W && py < p.H;
+            const uint32_t j = wt.ord[pix];
+            uint32_t col = q.clear_color;
+            if (MODE == MODE_RMW) {
+                if (tma) col = wt.color[pix];
+                else if (in_frame && j != ORD_NONE) col = q.color[(size_t)f * q.frame_stride + (size_t)py * p.W + px];
+            }
+            if (j != ORD_NONE) {
+                const float4* rec = list + (size_t)j * 4;
+                const float4 r0 = __ldg(rec), r1 = __ldg(rec + 1), r2 = __ldg(rec + 2), r3 = __ldg(rec + 3);
+                float ux, uy, su, w0, w1, w2;
+                coverage_test(r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w, (float)px, (float)py, ux, uy, su);
+                barycentric_weights(ux, uy, su, r1.z, r3.w, w0, w1, w2);
+                const float4* ap = p.tri_attr + ((size_t)f * p.tri_cap + __float_as_uint(r2.z)) * NQ;
+                const float4 rw = __ldg(ap);
+                VaryingWeights vw = varying_weights(w0, w1, w2, rw.x, rw.y, rw.z);
+                float a[(NQ - 1) * 4];
+#pragma unroll
+                for (int k = 0; k < NQ - 1; k++) {
+                    float4 v = __ldg(ap + 1 + k);
+                    a[4 * k] = v.x;
+                    a[4 * k + 1] = v.y;
+                    a[4 * k + 2] = v.z;
+                    a[4 * k + 3] = v.w;
+                }
+                float attr[NA];
+#pragma unroll
+                for (int k = 0; k < NA; k++) attr[k] = interp(vw, a[3 * k], a[3 * k + 1], a[3 * k + 2]);
+                float rgb[3];
+                fragment_shader<SHADER>(p.uniforms[f], attr, q.diffuse, q.normal, sh, rgb);
+                col = (col & 0xFF000000u) | colour_bytes(rgb); /* alpha is never written: renderbuffer.cpp:38-44 */
+                if (q.primid && f == 0) q.primid[(size_t)py * p.W + px] = __float_as_uint(r2.w);
+            }
+            if (q.pixels_covered) covered_acc += __popc(__ballot_sync(FULL, j != ORD_NONE));
+            if (tma) {
+                if (MODE == MODE_SHADOW_R8) wt.r8[pix] = (uint8_t)(j != ORD_NONE ? (col & 255u) : 0u);
+                else wt.color[pix] = col;
+            } else if (in_frame) {
+                if (MODE == MODE_SHADOW_R8) {
+                    q.shadow_out[(size_t)f * q.shadow_out_frame_stride + (size_t)py * q.shadow_out_pitch + px] =
+                        (uint8_t)(j != ORD_NONE ? (col & 255u) : 0u);
+                } else if (MODE == MODE_CLEAR_FOLD || j != ORD_NONE) {
+                    const size_t o = (size_t)f * q.frame_stride + (size_t)py * p.W + px;
+                    q.color[o] = col;
+                    q.depth[o] = wt.depth[pix];
+                }
+            }
+        }
+        if (q.pixels_covered && lane == 0 && covered_acc) atomicAdd(q.pixels_covered + f, covered_acc);
 
-        /* -- flush -- */
+        /* -- flush: lane 0 hands the warp's tile to the TMA engine -- */
         if (tma) {
-            if (MODE != MODE_RMW) {
-                if (tid == 0) tma_wait_read0(); /* previous tile's store has drained the staging tile */
-                __syncthreads();
-            }
-            if (MODE == MODE_SHADOW_R8) {
-                sm.out_r8[ly * TILE + lx] = (uint8_t)(bkey >= 0 ? (bcol & 255u) : 0u);
-            } else {
-                sm.out_color[ly * TILE + lx] = bcol;
-                sm.out_depth[ly * TILE + lx] = bz;
-            }
             fence_async_smem();
-        } else if (in_frame) {
-            if (MODE == MODE_SHADOW_R8) {
-                q.shadow_out[(size_t)f * q.shadow_out_frame_stride + (size_t)py * q.shadow_out_pitch + px] =
-                    (uint8_t)(bkey >= 0 ? (bcol & 255u) : 0u);
-            } else if (MODE == MODE_CLEAR_FOLD || bkey >= 0) {
-                size_t o = (size_t)f * q.frame_stride + (size_t)py * p.W + px;
-                q.color[o] = bcol;
-                q.depth[o] = bz;
+            __syncwarp();
+            if (lane == 0) {
+                if (MODE == MODE_SHADOW_R8) {
+                    tma_store_3d(&tm_r8, wt.r8, X0, Y0, f);
+                } else {
+                    tma_store_3d(&tm_color, wt.color, X0, Y0, f);
+                    tma_store_3d(&tm_depth, wt.depth, X0, Y0, f);
+                }
+                tma_commit();
             }
         }
-        if (q.pixels_covered && lane == 0 && covered_acc) {
-            atomicAdd(q.pixels_covered + f, covered_acc);
-            covered_acc = 0;
+        /* clear duty while raster work remains: 32 (frame,tile) slots per tile rasterised */
+        if (MODE != MODE_RMW && !clear_done) {
+            const uint32_t base = __shfl_sync(FULL, clr_base, 0);
+            if (base >= n_slots) clear_done = true;
+            else clear_slots<MODE>(q, sm, tm_color, tm_depth, tm_r8, base, n_slots);
         }
-        /* advance the queue: publish the prefetched entry, start the load of the one after it */
-        if (tid == 0) {
-            sm.cur = next_entry;
-            next_entry = fetch_work(p, next_idx, n_work);
-        }
-        __syncthreads(); /* end of tile: staging tile complete, sm.cur published, sm.tri free */
-        if (tma && tid == 0) {
-            if (MODE == MODE_SHADOW_R8) {
-                tma_store_3d(&tm_r8, sm.out_r8, tx * TILE, ty * TILE, f);
-            } else {
-                tma_store_3d(&tm_color, sm.out_color, tx * TILE, ty * TILE, f);
-                tma_store_3d(&tm_depth, sm.out_depth, tx * TILE, ty * TILE, f);
-            }
-            tma_commit();
-        }
+        /* advance the queue */
+        e_cur = e_nxt;
+        i_next = i_nn;
     }
     /* raster queue drained: every warp helps with what is left of the clear queue */
-    if (MODE != MODE_RMW)
-        while (!clear_done) clear_done = clear_slots<MODE>(q, sm, tm_color, tm_depth, tm_r8, n_slots);
+    if (MODE != MODE_RMW) {
+        while (!clear_done) {
+            uint32_t base = 0;
+            if (lane == 0) base = atomicAdd(&p.counters->clear_cursor, 32u);
+            base = __shfl_sync(FULL, base, 0);
+            if (base >= n_slots) clear_done = true;
+            else clear_slots<MODE>(q, sm, tm_color, tm_depth, tm_r8, base, n_slots);
+        }
+    }
     /* shared memory must outlive the bulk stores that read it */
     tma_wait_read0();
 }
