@@ -6,5 +6,5 @@ tail -5 gpurun_out/bench_v3.err
 python - <<'PY'
 import json
 d=json.load(open('gpurun_out/bench_v3.json'))
-print(d['value'], d['us_per_frame'], d['e2e']['value'], d['kernel_ms_per_step'], d['roofline']['frac'], d['frame_roofline']['frac'])
+print(d['value'], d['us_per_frame'], 'e2e', d['e2e']['value'], d['e2e_color_depth']['value'], d['kernel_ms_per_step'], d['roofline']['frac'], d['frame_roofline']['frac'], 'ms/step', d['ms_per_step'])
 PY

@@ -124,7 +124,7 @@ def load():
         "hana_sweep_create": [vp, i, i, i, C.POINTER(vp)],
         "hana_sweep_destroy": [vp],
         "hana_sweep_render": [vp, vp, i, vp, i, vp, vp, vp, f],
-        "hana_sweep_render_dev": [vp, vp, i, vp, i, vp, vp, vp, f],
+        "hana_sweep_render_dev": [vp, vp, i, vp, i, i, vp, vp, vp, f],
         "hana_sweep_uniforms_dev": [vp, C.POINTER(vp)],
         "hana_sweep_download": [vp, i, vp, vp],
         "hana_sweep_download_async": [vp, i, i, vp, vp],
@@ -382,13 +382,13 @@ class Sweep:
         return n
 
     def render_resident(self, model, shader, n_frames, diffuse=None, normal=None, clear_rgba=(0, 0, 0, 1),
-                        clear_depth=FLT_MAX):
+                        clear_depth=FLT_MAX, enable_shadow=True):
         """Uniforms already in the sweep's device buffer (from an earlier render())."""
         dev = C.c_void_p()
         _ck(self.ctx.L.hana_sweep_uniforms_dev(self.h, C.byref(dev)))
         clr = (C.c_uint8 * 4)(*clear_rgba)
-        _ck(self.ctx.L.hana_sweep_render_dev(self.h, model.h, shader, dev, n_frames, _h(diffuse), _h(normal), clr,
-                                             float(clear_depth)))
+        _ck(self.ctx.L.hana_sweep_render_dev(self.h, model.h, shader, dev, int(bool(enable_shadow)), n_frames, _h(diffuse),
+                                             _h(normal), clr, float(clear_depth)))
 
     def download(self, frame):
         color = np.empty((self.height, self.width, 4), np.uint8)

@@ -73,6 +73,8 @@ struct hana_ctx {
     int sm_count = 148;
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr; /* device->host frame copies, so that they overlap the next batch's kernels */
+    std::vector<hana_sweep*> sweeps;
     uint64_t launches = 0;
     bool use_tma = true;
     EncodeTiledFn encode = nullptr;
@@ -136,6 +138,26 @@ struct hana_sweep {
     float last_clear_depth;
     HanaStats last_stats; /* frame-independent part */
     std::vector<uint32_t> last_tri_counts[2];
+    /* asynchronous rendering: a render is launched without any read-back; what it needed is checked (and the batch
+     * re-rendered with larger scratch if something was dropped) at the sweep's next synchronisation point */
+    OverflowRecord* overflow;      /* device */
+    struct Pinned {
+        OverflowRecord need;
+        PassCounters counters[2];
+    }* pin;                        /* pinned host */
+    uint32_t* tri_counts_pin;      /* pinned host: [2][max_frames] */
+    cudaEvent_t ev_render, ev_copy;
+    bool copy_in_flight;
+    struct Pending {
+        bool active = false;
+        const hana_model* model = nullptr;
+        int shader = 0, enable_shadow = 0, n_frames = 0;
+        const hana_texture* diffuse = nullptr;
+        const hana_texture* normal = nullptr;
+        uint8_t clear_rgba[4] = {0, 0, 0, 0};
+        float clear_depth = 0.f;
+        uint32_t tri_cap = 0, pool_cap = 0;
+    } pending;
 };
 
 extern "C" const char* hana_last_error(void) { return g_err.c_str(); }
@@ -198,6 +220,7 @@ extern "C" int hana_ctx_create(int device, hana_ctx** out) {
     }
     ctx->sm_count = prop.multiProcessorCount;
     CU_TRY(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
+    CU_TRY(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
     ctx->stream = ctx->own_stream;
     void* fn = nullptr;
     cudaDriverEntryPointQueryResult qr;
@@ -237,6 +260,7 @@ extern "C" int hana_ctx_destroy(hana_ctx* ctx) {
     for (auto e : ctx->ev_pool) cudaEventDestroy(e);
     cudaEventDestroy(ctx->t0); cudaEventDestroy(ctx->t1);
     cudaStreamDestroy(ctx->own_stream);
+    cudaStreamDestroy(ctx->copy_stream);
     delete ctx;
     return HANA_OK;
 }
@@ -248,10 +272,13 @@ extern "C" int hana_ctx_set_stream(hana_ctx* ctx, void* cuda_stream) {
     ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
     return HANA_OK;
 }
+static int sweep_verify(hana_sweep* s);
 extern "C" int hana_sync(hana_ctx* ctx) {
     if (!ctx) return fail(HANA_E_INVALID, "ctx is NULL");
     HANA_TRY(use_device(ctx));
+    for (hana_sweep* s : ctx->sweeps) HANA_TRY(sweep_verify(s)); /* re-renders a batch that ran out of scratch */
     CU_TRY(cudaStreamSynchronize(ctx->stream));
+    CU_TRY(cudaStreamSynchronize(ctx->copy_stream));
     return HANA_OK;
 }
 extern "C" int hana_ctx_launch_count(hana_ctx* ctx, uint64_t* out) {
@@ -337,6 +364,10 @@ extern "C" int hana_timer_start(hana_ctx* ctx) {
 extern "C" int hana_timer_stop(hana_ctx* ctx, float* ms) {
     if (!ctx || !ms) return fail(HANA_E_INVALID, "NULL argument");
     HANA_TRY(use_device(ctx));
+    for (hana_sweep* s : ctx->sweeps) { /* the timed region ends when checked frames (and their copies) are complete */
+        HANA_TRY(sweep_verify(s));
+        if (s->copy_in_flight) CU_TRY(cudaStreamWaitEvent(ctx->stream, s->ev_copy, 0));
+    }
     CU_TRY(cudaEventRecord(ctx->t1, ctx->stream));
     CU_TRY(cudaEventSynchronize(ctx->t1));
     CU_TRY(cudaEventElapsedTime(ms, ctx->t0, ctx->t1));
@@ -560,6 +591,14 @@ struct PassDesc {
     int prof_kind = PROF_RASTER_MAIN;
     std::vector<uint32_t>* tri_counts_out = nullptr;
     PassCounters* counters_out = nullptr;
+    /* lazy mode (sweeps): nothing is read back inside the pass; capacities are the context's current ones and the
+     * needs are accumulated in *overflow for the host to check at the sweep's next synchronisation point */
+    bool lazy = false;
+    OverflowRecord* overflow = nullptr;
+    uint32_t* tri_counts_pinned = nullptr; /* lazy: [n_frames], filled asynchronously */
+    PassCounters* counters_pinned = nullptr;
+    uint32_t* tri_cap_used = nullptr;      /* lazy: capacities this pass ran with */
+    uint32_t* pool_cap_used = nullptr;
 };
 
 template <typename T>
@@ -663,6 +702,7 @@ static int run_pass(hana_ctx* ctx, const PassDesc& d) {
         p.pool_cap = (uint32_t)std::min<size_t>(sc.pool_cap / 4, 0xFFFFFFFFull);
         p.work = sc.work;
         p.counters = sc.counters;
+        p.overflow = d.overflow;
         p.dbg_v2f = d.dbg_v2f;
 
         /* zero: counters, per-frame triangle counts, tile counts + cursors (contiguous) */
@@ -695,6 +735,22 @@ static int run_pass(hana_ctx* ctx, const PassDesc& d) {
         prof_end(ctx, PROF_SCAN, ea, eb);
         ctx->launches++;
         CU_TRY(cudaGetLastError());
+        if (d.lazy) { /* no read-back: run with what we have, the sweep verifies afterwards */
+            PassCounters& c = *sc.counters_host;
+            memset(&c, 0, sizeof(c));
+            c.tri_needed = tri_cap;
+            c.pool_used = 1;
+            c.n_work = 0xFFFFFFFFu;
+            if (d.counters_pinned)
+                CU_TRY(cudaMemcpyAsync(d.counters_pinned, sc.counters, sizeof(PassCounters), cudaMemcpyDeviceToHost, ctx->stream));
+            if (d.tri_counts_pinned)
+                CU_TRY(cudaMemcpyAsync(d.tri_counts_pinned, sc.tri_count, sizeof(uint32_t) * d.n_frames, cudaMemcpyDeviceToHost,
+                                       ctx->stream));
+            if (d.tri_cap_used) *d.tri_cap_used = tri_cap;
+            if (d.pool_cap_used) *d.pool_cap_used = p.pool_cap;
+            lists_ready = true;
+            break;
+        }
         CU_TRY(cudaMemcpyAsync(sc.counters_host, sc.counters, sizeof(PassCounters), cudaMemcpyDeviceToHost, ctx->stream));
         CU_TRY(cudaStreamSynchronize(ctx->stream));
         const PassCounters& c = *sc.counters_host;
@@ -714,7 +770,7 @@ static int run_pass(hana_ctx* ctx, const PassDesc& d) {
     if (!lists_ready) return fail(HANA_E_OVERFLOW, "triangle capacity still exceeded after retries");
     const PassCounters cnt = *sc.counters_host;
     if (d.counters_out) *d.counters_out = cnt;
-    if (d.tri_counts_out) {
+    if (d.tri_counts_out && !d.lazy) {
         d.tri_counts_out->resize(d.n_frames);
         CU_TRY(cudaMemcpyAsync(d.tri_counts_out->data(), sc.tri_count, sizeof(uint32_t) * d.n_frames, cudaMemcpyDeviceToHost,
                                ctx->stream));
@@ -934,7 +990,8 @@ extern "C" int hana_sweep_create(hana_ctx* ctx, int width, int height, int max_f
     s->shadow_pitch = (width + 15) / 16 * 16;
     s->shadow_frame_bytes = (size_t)s->shadow_pitch * ((height + 15) / 16 * 16);
     s->color = nullptr; s->depth = nullptr; s->shadow_r8 = nullptr; s->u_raw = nullptr; s->u_dev = nullptr;
-    s->checksums = nullptr; s->pix_counts = nullptr;
+    s->checksums = nullptr; s->pix_counts = nullptr; s->overflow = nullptr; s->pin = nullptr; s->tri_counts_pin = nullptr;
+    s->ev_render = nullptr; s->ev_copy = nullptr; s->copy_in_flight = false;
     cudaError_t e = cudaMalloc(&s->color, n * 4 * max_frames);
     if (e == cudaSuccess) e = cudaMalloc(&s->depth, n * 4 * max_frames);
     if (e == cudaSuccess) e = cudaMalloc(&s->shadow_r8, s->shadow_frame_bytes * max_frames);
@@ -942,11 +999,17 @@ extern "C" int hana_sweep_create(hana_ctx* ctx, int width, int height, int max_f
     if (e == cudaSuccess) e = cudaMalloc(&s->u_dev, sizeof(DevUniforms) * max_frames);
     if (e == cudaSuccess) e = cudaMalloc(&s->checksums, sizeof(unsigned long long) * max_frames);
     if (e == cudaSuccess) e = cudaMalloc(&s->pix_counts, sizeof(uint32_t) * max_frames);
+    if (e == cudaSuccess) e = cudaMalloc(&s->overflow, sizeof(OverflowRecord));
+    if (e == cudaSuccess) e = cudaMallocHost(&s->pin, sizeof(*s->pin));
+    if (e == cudaSuccess) e = cudaMallocHost(&s->tri_counts_pin, sizeof(uint32_t) * 2 * max_frames);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev_render, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev_copy, cudaEventDisableTiming);
     if (e != cudaSuccess) {
         cudaGetLastError();
         hana_sweep_destroy(s);
-        return fail(HANA_E_CUDA, std::string("cudaMalloc failed for the frame ring: ") + cudaGetErrorString(e));
+        return fail(HANA_E_CUDA, std::string("allocation failed for the frame ring: ") + cudaGetErrorString(e));
     }
+    memset(s->pin, 0, sizeof(*s->pin));
     s->tma_ok = false;
     if (ctx->encode && width % 4 == 0) {
         int r1 = make_tensor_map(ctx, &s->tm_color, CU_TENSOR_MAP_DATA_TYPE_UINT32, 4, s->color, width, height, max_frames,
@@ -957,25 +1020,33 @@ extern "C" int hana_sweep_create(hana_ctx* ctx, int width, int height, int max_f
                                  (uint64_t)s->shadow_pitch, (uint64_t)s->shadow_frame_bytes);
         s->tma_ok = (r1 == HANA_OK && r2 == HANA_OK && r3 == HANA_OK);
     }
+    ctx->sweeps.push_back(s);
     *out = s;
     return HANA_OK;
 }
 extern "C" int hana_sweep_destroy(hana_sweep* s) {
     if (!s) return HANA_OK;
-    cudaSetDevice(s->ctx->device);
-    cudaStreamSynchronize(s->ctx->stream);
+    hana_ctx* ctx = s->ctx;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    cudaStreamSynchronize(ctx->copy_stream);
     cudaFree(s->color); cudaFree(s->depth); cudaFree(s->shadow_r8); cudaFree(s->u_raw); cudaFree(s->u_dev);
-    cudaFree(s->checksums); cudaFree(s->pix_counts);
-    if (s->ctx->host_sweep == s) s->ctx->host_sweep = nullptr;
+    cudaFree(s->checksums); cudaFree(s->pix_counts); cudaFree(s->overflow);
+    if (s->pin) cudaFreeHost(s->pin);
+    if (s->tri_counts_pin) cudaFreeHost(s->tri_counts_pin);
+    if (s->ev_render) cudaEventDestroy(s->ev_render);
+    if (s->ev_copy) cudaEventDestroy(s->ev_copy);
+    if (ctx->host_sweep == s) ctx->host_sweep = nullptr;
+    ctx->sweeps.erase(std::remove(ctx->sweeps.begin(), ctx->sweeps.end(), s), ctx->sweeps.end());
     delete s;
     return HANA_OK;
 }
 
-static int sweep_render_common(hana_sweep* s, const hana_model* model, int shader_id, const HanaUniforms* host_uniforms,
-                               int enable_shadow, int n_frames, const hana_texture* diffuse, const hana_texture* normal,
-                               const uint8_t clear_rgba[4], float clear_depth) {
+/* Both passes of every frame of the batch (scene.h:73-91). lazy: launch everything without reading anything back. */
+static int sweep_render_passes(hana_sweep* s, const hana_model* model, int shader_id, int enable_shadow, int n_frames,
+                               const hana_texture* diffuse, const hana_texture* normal, const uint8_t clear_rgba[4],
+                               float clear_depth, bool lazy) {
     hana_ctx* ctx = s->ctx;
-    HANA_TRY(upload_uniforms(ctx, host_uniforms, n_frames, s->u_raw, s->u_dev));
     PassCounters cnt[2];
     memset(cnt, 0, sizeof(cnt));
     if (enable_shadow) { /* scene.h:73-88, into the internal R8 maps */
@@ -996,6 +1067,12 @@ static int sweep_render_common(hana_sweep* s, const hana_model* model, int shade
         d.prof_kind = PROF_RASTER_SHADOW;
         d.counters_out = &cnt[0];
         d.tri_counts_out = &s->last_tri_counts[0];
+        d.lazy = lazy;
+        d.overflow = s->overflow;
+        d.tri_counts_pinned = s->tri_counts_pin;
+        d.counters_pinned = &s->pin->counters[0];
+        d.tri_cap_used = &s->pending.tri_cap;
+        d.pool_cap_used = &s->pending.pool_cap;
         HANA_TRY(run_pass(ctx, d));
     }
     PassDesc d;
@@ -1028,13 +1105,75 @@ static int sweep_render_common(hana_sweep* s, const hana_model* model, int shade
     d.prof_kind = PROF_RASTER_MAIN;
     d.counters_out = &cnt[1];
     d.tri_counts_out = &s->last_tri_counts[1];
+    d.lazy = lazy;
+    d.overflow = s->overflow;
+    d.tri_counts_pinned = s->tri_counts_pin + s->max_frames;
+    d.counters_pinned = &s->pin->counters[1];
+    uint32_t tc = 0, pc = 0;
+    d.tri_cap_used = &tc;
+    d.pool_cap_used = &pc;
     HANA_TRY(run_pass(ctx, d));
+    if (lazy) { /* the smaller of the two passes' capacities is what both must fit */
+        if (!enable_shadow || tc < s->pending.tri_cap) s->pending.tri_cap = tc;
+        if (!enable_shadow || pc < s->pending.pool_cap) s->pending.pool_cap = pc;
+    }
     s->last_frames = n_frames;
     s->last_clear_depth = clear_depth;
     memset(&s->last_stats, 0, sizeof(s->last_stats));
     s->last_stats.faces_in = (uint32_t)(model->ncorners / 3);
     s->last_stats.tile_refs = cnt[1].pool_used;
     s->last_stats.tiles_touched = cnt[1].tiles_touched;
+    return HANA_OK;
+}
+
+/* The sweep's synchronisation point: waits for its last render, and if that render ran out of scratch (triangles
+ * or tile-list records were dropped), grows the scratch and renders the batch again, this time with read-backs. */
+static int sweep_verify(hana_sweep* s) {
+    hana_ctx* ctx = s->ctx;
+    if (!s->pending.active) return HANA_OK;
+    CU_TRY(cudaEventSynchronize(s->ev_render));
+    hana_sweep::Pending pd = s->pending;
+    s->pending.active = false;
+    const OverflowRecord need = s->pin->need;
+    for (int pass = 0; pass < 2; pass++) {
+        s->last_tri_counts[pass].assign(s->tri_counts_pin + (size_t)pass * s->max_frames,
+                                        s->tri_counts_pin + (size_t)pass * s->max_frames + pd.n_frames);
+    }
+    s->last_stats.tile_refs = s->pin->counters[1].pool_used;
+    s->last_stats.tiles_touched = s->pin->counters[1].tiles_touched;
+    if (need.tri_needed <= pd.tri_cap && need.pool_needed <= pd.pool_cap) return HANA_OK;
+    ctx->tri_cap_hint = std::max(ctx->tri_cap_hint, need.tri_needed + need.tri_needed / 8 + 64);
+    if ((size_t)need.pool_needed > ctx->sc.pool_cap / 4) /* headroom for the other frames of an orbit */
+        HANA_TRY(grow(&ctx->sc.tile_recs, &ctx->sc.pool_cap, ((size_t)need.pool_needed + need.pool_needed / 4) * 4, ctx));
+    return sweep_render_passes(s, pd.model, pd.shader, pd.enable_shadow, pd.n_frames, pd.diffuse, pd.normal, pd.clear_rgba,
+                               pd.clear_depth, false);
+}
+
+static int sweep_render_common(hana_sweep* s, const hana_model* model, int shader_id, const HanaUniforms* host_uniforms,
+                               int enable_shadow, int n_frames, const hana_texture* diffuse, const hana_texture* normal,
+                               const uint8_t clear_rgba[4], float clear_depth) {
+    hana_ctx* ctx = s->ctx;
+    /* the previous render's frames are about to be overwritten: nothing to verify, but its copies must be out */
+    s->pending.active = false;
+    if (s->copy_in_flight) {
+        CU_TRY(cudaStreamWaitEvent(ctx->stream, s->ev_copy, 0));
+        s->copy_in_flight = false;
+    }
+    HANA_TRY(upload_uniforms(ctx, host_uniforms, n_frames, s->u_raw, s->u_dev));
+    CU_TRY(cudaMemsetAsync(s->overflow, 0, sizeof(OverflowRecord), ctx->stream));
+    HANA_TRY(sweep_render_passes(s, model, shader_id, enable_shadow, n_frames, diffuse, normal, clear_rgba, clear_depth, true));
+    CU_TRY(cudaMemcpyAsync(&s->pin->need, s->overflow, sizeof(OverflowRecord), cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(cudaEventRecord(s->ev_render, ctx->stream));
+    hana_sweep::Pending& pd = s->pending;
+    pd.active = true;
+    pd.model = model;
+    pd.shader = shader_id;
+    pd.enable_shadow = enable_shadow;
+    pd.n_frames = n_frames;
+    pd.diffuse = diffuse;
+    pd.normal = normal;
+    memcpy(pd.clear_rgba, clear_rgba, 4);
+    pd.clear_depth = clear_depth;
     return HANA_OK;
 }
 
@@ -1054,8 +1193,8 @@ extern "C" int hana_sweep_render(hana_sweep* s, const hana_model* model, int sha
 }
 
 extern "C" int hana_sweep_render_dev(hana_sweep* s, const hana_model* model, int shader_id, const void* uniforms_dev,
-                                     int n_frames, const hana_texture* diffuse, const hana_texture* normal,
-                                     const uint8_t clear_rgba[4], float clear_depth) {
+                                     int enable_shadow, int n_frames, const hana_texture* diffuse,
+                                     const hana_texture* normal, const uint8_t clear_rgba[4], float clear_depth) {
     if (!s || !uniforms_dev || !model || !clear_rgba) return fail(HANA_E_INVALID, "NULL argument");
     if (model->ctx != s->ctx) return fail(HANA_E_INVALID, "model belongs to another context");
     if (shader_id < 0 || shader_id >= HANA_SHADER_COUNT) return fail(HANA_E_UNSUPPORTED, "shader id outside the device set");
@@ -1064,11 +1203,8 @@ extern "C" int hana_sweep_render_dev(hana_sweep* s, const hana_model* model, int
     HANA_TRY(use_device(ctx));
     if (uniforms_dev != s->u_raw)
         CU_TRY(cudaMemcpyAsync(s->u_raw, uniforms_dev, sizeof(HanaUniforms) * n_frames, cudaMemcpyDeviceToDevice, ctx->stream));
-    int32_t enable = 0; /* frame 0 decides for the batch */
-    CU_TRY(cudaMemcpyAsync(&enable, reinterpret_cast<const char*>(s->u_raw) + offsetof(HanaUniforms, enable_shadow), 4,
-                           cudaMemcpyDeviceToHost, ctx->stream));
-    CU_TRY(cudaStreamSynchronize(ctx->stream));
-    return sweep_render_common(s, model, shader_id, nullptr, enable != 0, n_frames, diffuse, normal, clear_rgba, clear_depth);
+    return sweep_render_common(s, model, shader_id, nullptr, enable_shadow != 0, n_frames, diffuse, normal, clear_rgba,
+                               clear_depth);
 }
 
 extern "C" int hana_sweep_uniforms_dev(hana_sweep* s, void** out) {
@@ -1081,6 +1217,7 @@ extern "C" int hana_sweep_download(hana_sweep* s, int frame, uint8_t* color_rgba
     if (!s) return fail(HANA_E_INVALID, "sweep is NULL");
     if (frame < 0 || frame >= s->max_frames) return fail(HANA_E_INVALID, "frame out of range");
     HANA_TRY(use_device(s->ctx));
+    HANA_TRY(sweep_verify(s));
     size_t n = (size_t)s->w * s->h;
     if (color_rgba)
         CU_TRY(cudaMemcpyAsync(color_rgba, s->color + n * frame, n * 4, cudaMemcpyDeviceToHost, s->ctx->stream));
@@ -1088,19 +1225,29 @@ extern "C" int hana_sweep_download(hana_sweep* s, int frame, uint8_t* color_rgba
     CU_TRY(cudaStreamSynchronize(s->ctx->stream));
     return HANA_OK;
 }
+/* Copies on the context's copy stream, after the sweep's render: the next batch (into another sweep) overlaps them.
+ * Complete at hana_sync(). */
 extern "C" int hana_sweep_download_async(hana_sweep* s, int first, int count, uint8_t* color_rgba_pinned, float* depth_pinned) {
     if (!s) return fail(HANA_E_INVALID, "sweep is NULL");
     if (first < 0 || count < 0 || first + count > s->max_frames) return fail(HANA_E_INVALID, "frame range out of bounds");
-    HANA_TRY(use_device(s->ctx));
+    hana_ctx* ctx = s->ctx;
+    HANA_TRY(use_device(ctx));
+    HANA_TRY(sweep_verify(s)); /* host waits for the render (not for any copy) so that only checked frames leave */
+    CU_TRY(cudaEventRecord(s->ev_render, ctx->stream));
+    CU_TRY(cudaStreamWaitEvent(ctx->copy_stream, s->ev_render, 0));
     size_t n = (size_t)s->w * s->h;
     if (color_rgba_pinned)
-        CU_TRY(cudaMemcpyAsync(color_rgba_pinned, s->color + n * first, n * 4 * count, cudaMemcpyDeviceToHost, s->ctx->stream));
+        CU_TRY(cudaMemcpyAsync(color_rgba_pinned, s->color + n * first, n * 4 * count, cudaMemcpyDeviceToHost, ctx->copy_stream));
     if (depth_pinned)
-        CU_TRY(cudaMemcpyAsync(depth_pinned, s->depth + n * first, n * 4 * count, cudaMemcpyDeviceToHost, s->ctx->stream));
+        CU_TRY(cudaMemcpyAsync(depth_pinned, s->depth + n * first, n * 4 * count, cudaMemcpyDeviceToHost, ctx->copy_stream));
+    CU_TRY(cudaEventRecord(s->ev_copy, ctx->copy_stream));
+    s->copy_in_flight = true;
     return HANA_OK;
 }
 extern "C" int hana_sweep_device_ptrs(hana_sweep* s, void** color_dev, void** depth_dev, size_t* frame_stride_pixels) {
     if (!s) return fail(HANA_E_INVALID, "sweep is NULL");
+    HANA_TRY(use_device(s->ctx));
+    HANA_TRY(sweep_verify(s));
     if (color_dev) *color_dev = s->color;
     if (depth_dev) *depth_dev = s->depth;
     if (frame_stride_pixels) *frame_stride_pixels = (size_t)s->w * s->h;
@@ -1111,6 +1258,7 @@ extern "C" int hana_sweep_checksums(hana_sweep* s, int n_frames, uint64_t* out_h
     if (n_frames < 1 || n_frames > s->max_frames) return fail(HANA_E_INVALID, "n_frames out of range");
     hana_ctx* ctx = s->ctx;
     HANA_TRY(use_device(ctx));
+    HANA_TRY(sweep_verify(s));
     CU_TRY(cudaMemsetAsync(s->checksums, 0, sizeof(unsigned long long) * n_frames, ctx->stream));
     size_t n = (size_t)s->w * s->h;
     dim3 grid((unsigned)std::min<size_t>((n + 255) / 256, 256), n_frames);
@@ -1129,6 +1277,7 @@ extern "C" int hana_sweep_stats(hana_sweep* s, int frame, HanaStats* out) {
     if (frame < 0 || frame >= s->last_frames) return fail(HANA_E_INVALID, "frame outside the last batch");
     hana_ctx* ctx = s->ctx;
     HANA_TRY(use_device(ctx));
+    HANA_TRY(sweep_verify(s));
     CU_TRY(cudaMemsetAsync(s->pix_counts, 0, sizeof(uint32_t) * s->last_frames, ctx->stream));
     size_t n = (size_t)s->w * s->h;
     dim3 grid((unsigned)std::min<size_t>((n + 255) / 256, 256), s->last_frames);

@@ -55,6 +55,14 @@ struct PassCounters {
     uint32_t pad[2];
 };
 
+/* Capacity needs of the last render of a sweep, kept across both passes (atomicMax): lets the host launch a whole
+ * batch without reading anything back in the middle and check afterwards that nothing was dropped. */
+struct OverflowRecord {
+    uint32_t tri_needed;  /* max over passes and frames of triangles emitted */
+    uint32_t pool_needed; /* max over passes of tile-list records */
+    uint32_t pad[2];
+};
+
 struct PassParams {
     /* geometry */
     const float4* posu;   /* per corner: obj_pos.xyz, uv.x */
@@ -75,6 +83,7 @@ struct PassParams {
     uint32_t pool_cap;    /* in records */
     uint4* work;          /* [n_frames*n_tiles] non-empty tiles: {item, count, offset, 0} */
     PassCounters* counters;
+    OverflowRecord* overflow; /* optional */
     float* dbg_v2f;       /* optional: [tri_cap][39] post-clip v2f of frame 0 (stage tests) */
 };
 
@@ -162,6 +171,8 @@ struct ShaderAttrs {
                                   ? 1
                                   : (SHADER == HANA_SHADER_TEXTURE ? 2 : (SHADER == HANA_SHADER_TEXTURE_LIGHT ? 5 : 8));
     static constexpr int NQ = 1 + (3 * NA + 3) / 4;
+    static constexpr bool LIT = (SHADER == HANA_SHADER_BLINN || SHADER == HANA_SHADER_NORMALMAP);
+    static constexpr bool READS_UNIFORMS = LIT || SHADER == HANA_SHADER_TEXTURE_LIGHT; /* in fragment() */
 };
 constexpr int MAX_ATTR_QUADS = 7;
 
@@ -326,6 +337,10 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_kernel(PassParams p) {
         s_base_work = atomicAdd(&p.counters->n_work, s_total_ne);
         atomicAdd(&p.counters->tiles_touched, s_total_ne);
         atomicMax(&p.counters->tri_needed, p.tri_count[f]);
+        if (p.overflow) {
+            atomicMax(&p.overflow->tri_needed, p.tri_count[f]);
+            atomicMax(&p.overflow->pool_needed, s_base_refs + s_total_refs);
+        }
     }
     __syncthreads();
     uint32_t off = s_base_refs + ex_refs;
@@ -342,32 +357,63 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_kernel(PassParams p) {
     }
 }
 
-/* ---- fill: raster records into the tile lists --------------------------------- */
+/* ---- fill: raster records into the tile lists ---------------------------------
+ * A lane owns one triangle, but the (triangle, tile) pairs of the whole warp are flattened by a
+ * shuffle prefix sum and dealt out round-robin, so every list-slot atomic of a round is independent
+ * (a triangle covering 100 tiles costs its warp 4 rounds instead of one lane 100 dependent ones). */
 __global__ void __launch_bounds__(256) fill_kernel(PassParams p) {
+    constexpr unsigned FULL = 0xFFFFFFFFu;
     const int f = blockIdx.y;
     const uint32_t i = blockIdx.x * 256u + threadIdx.x;
+    const unsigned lane = threadIdx.x & 31u;
     uint32_t n = p.tri_count[f];
     if (n > p.tri_cap) n = p.tri_cap;
-    if (i >= n) return;
+    if ((i & ~31u) >= n) return;                    /* whole warp past the end */
     if (p.counters->pool_used > p.pool_cap) return; /* host re-runs the pass with a larger pool */
-    const float4* rec = p.tri_rec + ((size_t)f * p.tri_cap + i) * 4;
-    const float4 q0 = __ldg(rec), q1 = __ldg(rec + 1), q2 = __ldg(rec + 2), q3 = __ldg(rec + 3);
-    uint32_t bbx = __float_as_uint(q2.x);
-    uint32_t bby = __float_as_uint(q2.y);
-    int tx0 = (int)(bbx & 0xFFFFu) >> 4, tx1 = (int)(bbx >> 16) >> 4;
-    int ty0 = (int)(bby & 0xFFFFu) >> 4, ty1 = (int)(bby >> 16) >> 4;
+    const float4* warp_rec = p.tri_rec + ((size_t)f * p.tri_cap + (i & ~31u)) * 4;
+    int tx0 = 0, ty0 = 0, ntx = 1, nt = 0;
+    if (i < n) {
+        const float4 q2 = __ldg(warp_rec + lane * 4 + 2);
+        const uint32_t bbx = __float_as_uint(q2.x), bby = __float_as_uint(q2.y);
+        tx0 = (int)(bbx & 0xFFFFu) >> 4;
+        ty0 = (int)(bby & 0xFFFFu) >> 4;
+        ntx = ((int)(bbx >> 16) >> 4) - tx0 + 1;
+        nt = ntx * (((int)(bby >> 16) >> 4) - ty0 + 1);
+    }
+    int incl = nt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int t = __shfl_up_sync(FULL, incl, d);
+        if ((int)lane >= d) incl += t;
+    }
+    const int excl = incl - nt;
+    const int total = __shfl_sync(FULL, incl, 31);
     uint32_t* cur = p.tile_cursor + (size_t)f * p.n_tiles;
     const uint32_t* to = p.tile_offset + (size_t)f * p.n_tiles;
-    for (int ty = ty0; ty <= ty1; ty++)
-        for (int tx = tx0; tx <= tx1; tx++) {
-            int t = ty * p.tiles_x + tx;
-            uint32_t s = atomicAdd(cur + t, 1u);
-            float4* d = p.tile_recs + ((size_t)to[t] + s) * 4;
+    for (int base = 0; base < total; base += 32) {
+        const int k = base + (int)lane;
+        /* owner of pair k: the last lane whose exclusive prefix is <= k (it has nt > 0 whenever k < total) */
+        int j = 0;
+#pragma unroll
+        for (int step = 16; step > 0; step >>= 1) {
+            const int e = __shfl_sync(FULL, excl, (j + step) & 31);
+            if (e <= k) j += step;
+        }
+        const int local = k - __shfl_sync(FULL, excl, j);
+        const int jtx0 = __shfl_sync(FULL, tx0, j), jty0 = __shfl_sync(FULL, ty0, j), jntx = __shfl_sync(FULL, ntx, j);
+        if (k < total) {
+            const float4* rec = warp_rec + j * 4;
+            const float4 q0 = __ldg(rec), q1 = __ldg(rec + 1), q2 = __ldg(rec + 2), q3 = __ldg(rec + 3);
+            const int row = local / jntx;
+            const int t = (jty0 + row) * p.tiles_x + jtx0 + (local - row * jntx);
+            const uint32_t s = atomicAdd(cur + t, 1u);
+            float4* d = p.tile_recs + ((size_t)__ldg(to + t) + s) * 4;
             d[0] = q0;
             d[1] = q1;
             d[2] = q2;
             d[3] = q3;
         }
+    }
 }
 
 /* ---- raster ------------------------------------------------------------------
@@ -394,6 +440,7 @@ struct alignas(128) WarpTile {
     uint8_t r8[MODE == MODE_SHADOW_R8 ? TILE_PIX : 128];    /* box 16x16 u8 */
     uint32_t ord[TILE_PIX];                                 /* winning list ordinal per pixel, parked for shading */
     float4 tri[RW_CHUNK * 4];                               /* staged raster records */
+    FragUniforms fu;                                        /* the tile's frame: what fragment() reads */
     alignas(8) uint64_t bar;
 };
 template <int MODE>
@@ -459,11 +506,59 @@ __device__ __forceinline__ uint32_t subblock_mask(uint32_t bbx, uint32_t bby, in
     return cm * spread;
 }
 
+/* graphics.cpp:362-370 for one fragment: interpolate the attributes the shader reads, run fragment(). The fragment
+ * stage's uniforms arrive as 11 128-bit loads. FAST: sqrt/reciprocal fast paths with one shared range check (qsqrt). */
+template <int SHADER, bool FAST>
+__device__ __forceinline__ bool shade_fragment_t(const FragUniforms& fu, const float4* ap, float w0, float w1, float w2,
+                                                 const DevTexture& diffuse, const DevTexture& normal, const DevShadow& sh,
+                                                 float rgb[3]) {
+    constexpr int NA = ShaderAttrs<SHADER>::NA;
+    constexpr int NQ = ShaderAttrs<SHADER>::NQ;
+    bool bad = false;
+    bool* pb = FAST ? &bad : nullptr;
+    const float4 rw = __ldg(ap);
+    VaryingWeights vw = varying_weights(w0, w1, w2, rw.x, rw.y, rw.z, pb);
+    float a[(NQ - 1) * 4];
+#pragma unroll
+    for (int k = 0; k < NQ - 1; k++) {
+        float4 v = __ldg(ap + 1 + k);
+        a[4 * k] = v.x;
+        a[4 * k + 1] = v.y;
+        a[4 * k + 2] = v.z;
+        a[4 * k + 3] = v.w;
+    }
+    float attr[NA];
+#pragma unroll
+    for (int k = 0; k < NA; k++) attr[k] = interp(vw, a[3 * k], a[3 * k + 1], a[3 * k + 2]);
+    fragment_shader<SHADER>(fu, attr, diffuse, normal, sh, rgb, pb);
+    return bad;
+}
+template <int SHADER>
+__device__ __noinline__ void shade_fragment_exact(const FragUniforms* fu, const float4* ap, float w0, float w1, float w2,
+                                                  const DevTexture* diffuse, const DevTexture* normal, const DevShadow* sh,
+                                                  float* rgb) {
+    float c[3];
+    shade_fragment_t<SHADER, false>(*fu, ap, w0, w1, w2, *diffuse, *normal, *sh, c);
+    rgb[0] = c[0];
+    rgb[1] = c[1];
+    rgb[2] = c[2];
+}
+template <int SHADER>
+__device__ __forceinline__ void shade_fragment(const FragUniforms& fu, const float4* ap, float w0, float w1, float w2,
+                                               const DevTexture& diffuse, const DevTexture& normal, const DevShadow& sh,
+                                               float rgb[3]) {
+    if (ShaderAttrs<SHADER>::LIT) { /* ten sqrt/reciprocal sites: worth the shared range check */
+        if (shade_fragment_t<SHADER, true>(fu, ap, w0, w1, w2, diffuse, normal, sh, rgb)) /* an operand left the fast paths' range */
+            shade_fragment_exact<SHADER>(&fu, ap, w0, w1, w2, &diffuse, &normal, &sh, rgb);
+    } else {
+        shade_fragment_t<SHADER, false>(fu, ap, w0, w1, w2, diffuse, normal, sh, rgb);
+    }
+}
+
 template <int SHADER, int MODE>
-__global__ void __launch_bounds__(RW_THREADS)
+__global__ void __launch_bounds__(RW_THREADS, ShaderAttrs<SHADER>::LIT ? 6 : 7)
     raster_kernel(RasterParams q, const __grid_constant__ CUtensorMap tm_color, const __grid_constant__ CUtensorMap tm_depth,
                   const __grid_constant__ CUtensorMap tm_r8) {
-    constexpr int NA = ShaderAttrs<SHADER>::NA;
     constexpr int NQ = ShaderAttrs<SHADER>::NQ;
     constexpr unsigned FULL = 0xFFFFFFFFu;
     __shared__ RasterSmem<MODE> sm;
@@ -522,6 +617,8 @@ __global__ void __launch_bounds__(RW_THREADS)
         const int X0 = tx * TILE, Y0 = ty * TILE;
         const uint32_t cnt = cur.y;
         const float4* list = p.tile_recs + (size_t)cur.z * 4;
+        if (ShaderAttrs<SHADER>::READS_UNIFORMS && lane < sizeof(FragUniforms) / 16) /* read again only after the __syncwarp()s of the record loop */
+            reinterpret_cast<float4*>(&wt.fu)[lane] = __ldg(reinterpret_cast<const float4*>(&p.uniforms[f].frag) + lane);
         const float fpx0 = (float)(X0 + lx), fpx1 = (float)(X0 + 8 + lx);
         const float fpy0 = (float)(Y0 + ly), fpy1 = (float)(Y0 + 4 + ly), fpy2 = (float)(Y0 + 8 + ly), fpy3 = (float)(Y0 + 12 + ly);
         const int ipx0 = X0 + lx, ipy0 = Y0 + ly;
@@ -644,22 +741,8 @@ __global__ void __launch_bounds__(RW_THREADS)
                 coverage_test(r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w, (float)px, (float)py, ux, uy, su);
                 barycentric_weights(ux, uy, su, r1.z, r3.w, w0, w1, w2);
                 const float4* ap = p.tri_attr + ((size_t)f * p.tri_cap + __float_as_uint(r2.z)) * NQ;
-                const float4 rw = __ldg(ap);
-                VaryingWeights vw = varying_weights(w0, w1, w2, rw.x, rw.y, rw.z);
-                float a[(NQ - 1) * 4];
-#pragma unroll
-                for (int k = 0; k < NQ - 1; k++) {
-                    float4 v = __ldg(ap + 1 + k);
-                    a[4 * k] = v.x;
-                    a[4 * k + 1] = v.y;
-                    a[4 * k + 2] = v.z;
-                    a[4 * k + 3] = v.w;
-                }
-                float attr[NA];
-#pragma unroll
-                for (int k = 0; k < NA; k++) attr[k] = interp(vw, a[3 * k], a[3 * k + 1], a[3 * k + 2]);
                 float rgb[3];
-                fragment_shader<SHADER>(p.uniforms[f], attr, q.diffuse, q.normal, sh, rgb);
+                shade_fragment<SHADER>(wt.fu, ap, w0, w1, w2, q.diffuse, q.normal, sh, rgb);
                 col = (col & 0xFF000000u) | colour_bytes(rgb); /* alpha is never written: renderbuffer.cpp:38-44 */
                 if (q.primid && f == 0) q.primid[(size_t)py * p.W + px] = __float_as_uint(r2.w);
             }

@@ -210,7 +210,13 @@ HANA_API int hana_last_stats(hana_ctx* ctx, HanaStats* out); /* synchronises */
  * frame clear (clear_rgba, clear_depth), optional shadow pass, main pass —
  * i.e. main.cpp:152-153 + DrawModel::draw — with the frame index as a grid
  * dimension, so launch latency is paid once per batch. Frames land in a
- * device ring of `n_frames` colour+depth targets. */
+ * device ring of `n_frames` colour+depth targets.
+ * Renders are ASYNCHRONOUS: the call returns once the batch is queued, without
+ * reading anything back. The sweep's next synchronising call (download*,
+ * checksums, stats, device_ptrs, hana_sync, hana_timer_stop) waits for it and,
+ * if the batch ran out of internal scratch, transparently renders it again
+ * with more. Model, textures and a device uniform buffer must stay alive and
+ * unchanged until then. */
 HANA_API int hana_sweep_create(hana_ctx* ctx, int width, int height, int max_frames, hana_sweep** out);
 HANA_API int hana_sweep_destroy(hana_sweep* s);
 /* uniforms: host array of n_frames HanaUniforms (copied H2D inside). */
@@ -220,15 +226,19 @@ HANA_API int hana_sweep_render(hana_sweep* s, const hana_model* model, int shade
 /* Device buffer (max_frames * sizeof(HanaUniforms)) a caller may fill itself and hand to
  * hana_sweep_render_dev to keep the whole submission free of host->device copies. */
 HANA_API int hana_sweep_uniforms_dev(hana_sweep* s, void** out);
-/* Same, uniforms already resident on the device (n_frames * sizeof(HanaUniforms)). */
+/* Same, uniforms already resident on the device (n_frames * sizeof(HanaUniforms)); enable_shadow is what the
+ * caller wrote into them (scene.h:73), passed separately so that nothing has to be read back. */
 HANA_API int hana_sweep_render_dev(hana_sweep* s, const hana_model* model, int shader_id,
-                          const void* uniforms_dev, int n_frames, const hana_texture* diffuse,
-                          const hana_texture* normal, const uint8_t clear_rgba[4], float clear_depth);
+                          const void* uniforms_dev, int enable_shadow, int n_frames,
+                          const hana_texture* diffuse, const hana_texture* normal,
+                          const uint8_t clear_rgba[4], float clear_depth);
 /* Copy frame `i` of the last batch to host (either may be NULL). Synchronous. */
 HANA_API int hana_sweep_download(hana_sweep* s, int frame, uint8_t* color_rgba, float* depth);
 /* Async copy of frames [first, first+count) into caller-provided PINNED host
- * memory (count*W*H*4 bytes each plane; depth may be NULL); ordered on the
- * context's stream. */
+ * memory (count*W*H*4 bytes each plane; either may be NULL). The host waits for
+ * the sweep's render, then the copies run on the context's copy stream so that
+ * the next batch (rendered into ANOTHER sweep) overlaps them; they are complete
+ * after hana_sync(). A later render into this sweep waits for them on the device. */
 HANA_API int hana_sweep_download_async(hana_sweep* s, int first, int count, uint8_t* color_rgba_pinned,
                               float* depth_pinned);
 HANA_API int hana_sweep_device_ptrs(hana_sweep* s, void** color_dev, void** depth_dev,

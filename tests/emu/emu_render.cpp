@@ -24,7 +24,7 @@ static void shade(const DevUniforms& u, const EmuTri& t, float w0, float w1, flo
     float attr[8];
     int na = shader_nattr(SHADER);
     for (int k = 0; k < na; k++) attr[k] = interp(vw, t.attr[3 * k], t.attr[3 * k + 1], t.attr[3 * k + 2]);
-    fragment_shader<SHADER>(u, attr, dt, nt, sm, rgb);
+    fragment_shader<SHADER>(u.frag, attr, dt, nt, sm, rgb);
 }
 
 extern "C" {

@@ -91,7 +91,7 @@ def main():
         ti = sum(a[0] for a in agg.values()) or 1
         ts = sum(a[1] for a in agg.values()) or 1
         print("== %s\n   warp instructions %d, samples %d" % (name[:90], ti, ts))
-        for loc, a in sorted(agg.items(), key=lambda kv: -kv[1][1])[:top]:
+        for loc, a in sorted(agg.items(), key=lambda kv: -kv[1][0 if "--by-inst" in sys.argv else 1])[:top]:
             st = sorted(a[2].items(), key=lambda kv: -kv[1])[:3]
             print("  %5.1f%% inst  %5.1f%% samples  %-24s %s" % (100.0 * a[0] / ti, 100.0 * a[1] / ts, loc,
                                                               " ".join("%s=%d" % (h[6:], v) for h, v in st)))
