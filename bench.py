@@ -31,7 +31,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 W, H = 1920, 1080
-FRAMES_PER_STEP = 64
+FRAMES_PER_STEP = 128
 ORBIT = 1024
 SCENE = "african_head"
 T_BLINN = 7  # texel bytes per main-pass fragment: 3 (diffuse BGR) + 4 (shadow-map RGBA8 texel), SURVEY.md §8(d)

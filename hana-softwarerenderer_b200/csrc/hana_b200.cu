@@ -66,6 +66,7 @@ struct Scratch {
     size_t work_cap = 0;
     PassCounters* counters = nullptr;
     PassCounters* counters_host = nullptr; /* pinned */
+    PassParams saved_p;                    /* what the binning phase of a split pass left for its raster phase */
 };
 
 struct hana_ctx {
@@ -79,6 +80,9 @@ struct hana_ctx {
     bool use_tma = true;
     EncodeTiledFn encode = nullptr;
     Scratch sc;
+    Scratch sc2;                          /* second set: the main pass is binned on side_stream beside the shadow pass */
+    cudaStream_t side_stream = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     uint32_t tri_cap_hint = 0;
     HanaUniforms* u_raw = nullptr;  /* device, 1 */
     DevUniforms* u_dev = nullptr;   /* device, 1 */
@@ -236,6 +240,11 @@ extern "C" int hana_ctx_create(int device, hana_ctx** out) {
     CU_TRY(cudaMalloc(&ctx->stat_pixels, sizeof(uint32_t)));
     CU_TRY(cudaMalloc(&ctx->sc.counters, sizeof(PassCounters)));
     CU_TRY(cudaMallocHost(&ctx->sc.counters_host, sizeof(PassCounters)));
+    CU_TRY(cudaMalloc(&ctx->sc2.counters, sizeof(PassCounters)));
+    CU_TRY(cudaMallocHost(&ctx->sc2.counters_host, sizeof(PassCounters)));
+    CU_TRY(cudaStreamCreateWithFlags(&ctx->side_stream, cudaStreamNonBlocking));
+    CU_TRY(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+    CU_TRY(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
     CU_TRY(cudaEventCreate(&ctx->t0));
     CU_TRY(cudaEventCreate(&ctx->t1));
     *out = ctx;
@@ -252,9 +261,13 @@ extern "C" int hana_ctx_destroy(hana_ctx* ctx) {
     if (ctx->host_sweep) hana_sweep_destroy(ctx->host_sweep);
     if (ctx->host_frame) hana_rb_destroy(ctx->host_frame);
     if (ctx->host_shadow) hana_rb_destroy(ctx->host_shadow);
-    Scratch& s = ctx->sc;
-    cudaFree(s.tri_rec); cudaFree(s.tri_attr); cudaFree(s.tri_count); cudaFree(s.tile_arrays);
-    cudaFree(s.tile_recs); cudaFree(s.work); cudaFree(s.counters); cudaFreeHost(s.counters_host);
+    for (Scratch* sp : {&ctx->sc, &ctx->sc2}) {
+        Scratch& s = *sp;
+        cudaFree(s.tri_rec); cudaFree(s.tri_attr); cudaFree(s.tri_count); cudaFree(s.tile_arrays);
+        cudaFree(s.tile_recs); cudaFree(s.work); cudaFree(s.counters); cudaFreeHost(s.counters_host);
+    }
+    cudaStreamDestroy(ctx->side_stream);
+    cudaEventDestroy(ctx->ev_fork); cudaEventDestroy(ctx->ev_join);
     cudaFree(ctx->u_raw); cudaFree(ctx->u_dev); cudaFree(ctx->stat_pixels);
     for (auto& p : ctx->prof_pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
     for (auto e : ctx->ev_pool) cudaEventDestroy(e);
@@ -295,7 +308,7 @@ extern "C" int hana_ctx_set_tma(hana_ctx* ctx, int enable) {
 extern "C" int hana_ctx_sm_count(hana_ctx* ctx) { return ctx ? ctx->sm_count : 0; }
 
 /* ---- profiling (CUDA events around each kernel class, on the launching stream) ---- */
-static void prof_begin(hana_ctx* ctx, int kind, cudaEvent_t* a, cudaEvent_t* b) {
+static void prof_begin(hana_ctx* ctx, int kind, cudaEvent_t* a, cudaEvent_t* b, cudaStream_t st = nullptr) {
     *a = *b = nullptr;
     if (!ctx->profile) return;
     auto get = [&]() {
@@ -310,12 +323,12 @@ static void prof_begin(hana_ctx* ctx, int kind, cudaEvent_t* a, cudaEvent_t* b) 
     };
     *a = get();
     *b = get();
-    cudaEventRecord(*a, ctx->stream);
+    cudaEventRecord(*a, st ? st : ctx->stream);
     (void)kind;
 }
-static void prof_end(hana_ctx* ctx, int kind, cudaEvent_t a, cudaEvent_t b) {
+static void prof_end(hana_ctx* ctx, int kind, cudaEvent_t a, cudaEvent_t b, cudaStream_t st = nullptr) {
     if (!a) return;
-    cudaEventRecord(b, ctx->stream);
+    cudaEventRecord(b, st ? st : ctx->stream);
     ctx->prof_pending.push_back({a, b, kind});
 }
 static void prof_resolve(hana_ctx* ctx) {
@@ -599,6 +612,10 @@ struct PassDesc {
     PassCounters* counters_pinned = nullptr;
     uint32_t* tri_cap_used = nullptr;      /* lazy: capacities this pass ran with */
     uint32_t* pool_cap_used = nullptr;
+    /* split passes (lazy only): phase 1 = setup + scan + fill on `stream` with scratch set `scratch`, phase 2 = raster */
+    int phase = 0;
+    int scratch = 0;
+    cudaStream_t stream = nullptr;
 };
 
 template <typename T>
@@ -607,6 +624,7 @@ static int grow(T** ptr, size_t* cap, size_t need, hana_ctx* ctx) {
     size_t n = std::max(need, *cap + *cap / 2);
     n = std::max<size_t>(n, 1);
     CU_TRY(cudaStreamSynchronize(ctx->stream));
+    CU_TRY(cudaStreamSynchronize(ctx->side_stream));
     if (*ptr) CU_TRY(cudaFree(*ptr));
     *ptr = nullptr;
     *cap = 0;
@@ -616,10 +634,10 @@ static int grow(T** ptr, size_t* cap, size_t need, hana_ctx* ctx) {
 }
 
 template <int MODE>
-static int launch_raster(hana_ctx* ctx, int shader, int blocks, const RasterParams& rp, const CUtensorMap& a,
+static int launch_raster(cudaStream_t st, int shader, int blocks, const RasterParams& rp, const CUtensorMap& a,
                          const CUtensorMap& b, const CUtensorMap& c) {
 #define HANA_RASTER_CASE(S) \
-    case S: raster_kernel<S, MODE><<<blocks, RW_THREADS, 0, ctx->stream>>>(rp, a, b, c); break;
+    case S: raster_kernel<S, MODE><<<blocks, RW_THREADS, 0, st>>>(rp, a, b, c); break;
     switch (shader) {
         HANA_RASTER_CASE(HANA_SHADER_SHADOW)
         HANA_RASTER_CASE(HANA_SHADER_BLINN)
@@ -661,7 +679,8 @@ static int run_pass(hana_ctx* ctx, const PassDesc& d) {
     if (tiles_x > 1024 || tiles_y > 1024) return fail(HANA_E_INVALID, "target larger than 16384 pixels on a side");
     if (d.n_frames < 1 || d.n_frames > 4096) return fail(HANA_E_INVALID, "1..4096 frames per batch");
     const int nfaces = d.model->ncorners / 3;
-    Scratch& sc = ctx->sc;
+    Scratch& sc = d.scratch ? ctx->sc2 : ctx->sc;
+    cudaStream_t st = d.stream ? d.stream : ctx->stream;
     const size_t tiles_total = n_tiles * d.n_frames;
     if (tiles_total > 0xFFFFFFF0ull) return fail(HANA_E_INVALID, "frames x tiles exceeds 32 bits");
 
@@ -671,6 +690,16 @@ static int run_pass(hana_ctx* ctx, const PassDesc& d) {
     memset(&p, 0, sizeof(p));
     RasterParams rp;
     bool lists_ready = false;
+    if (d.phase == 2) { /* raster phase of a split lazy pass: the lists are where phase 1 put them */
+        p = sc.saved_p;
+        tri_cap = p.tri_cap;
+        PassCounters& c = *sc.counters_host;
+        memset(&c, 0, sizeof(c));
+        c.tri_needed = tri_cap;
+        c.pool_used = 1;
+        c.n_work = 0xFFFFFFFFu;
+        lists_ready = true;
+    }
     for (int attempt = 0; attempt < 4 && !lists_ready; attempt++) {
         /* capacities */
         size_t tri_total = (size_t)tri_cap * d.n_frames;
@@ -706,16 +735,16 @@ static int run_pass(hana_ctx* ctx, const PassDesc& d) {
         p.dbg_v2f = d.dbg_v2f;
 
         /* zero: counters, per-frame triangle counts, tile counts + cursors (contiguous) */
-        CU_TRY(cudaMemsetAsync(sc.counters, 0, sizeof(PassCounters), ctx->stream));
-        CU_TRY(cudaMemsetAsync(sc.tri_count, 0, sizeof(uint32_t) * d.n_frames, ctx->stream));
-        CU_TRY(cudaMemsetAsync(sc.tile_arrays, 0, sizeof(uint32_t) * 2 * tiles_total, ctx->stream));
+        CU_TRY(cudaMemsetAsync(sc.counters, 0, sizeof(PassCounters), st));
+        CU_TRY(cudaMemsetAsync(sc.tri_count, 0, sizeof(uint32_t) * d.n_frames, st));
+        CU_TRY(cudaMemsetAsync(sc.tile_arrays, 0, sizeof(uint32_t) * 2 * tiles_total, st));
 
         cudaEvent_t ea, eb;
         if (nfaces > 0) {
             dim3 grid((nfaces + SETUP_THREADS - 1) / SETUP_THREADS, d.n_frames);
-            prof_begin(ctx, PROF_SETUP, &ea, &eb);
+            prof_begin(ctx, PROF_SETUP, &ea, &eb, st);
 #define HANA_SETUP_CASE(S) \
-    case S: setup_kernel<S><<<grid, SETUP_THREADS, 0, ctx->stream>>>(p); break;
+    case S: setup_kernel<S><<<grid, SETUP_THREADS, 0, st>>>(p); break;
             switch (d.shader) {
                 HANA_SETUP_CASE(HANA_SHADER_SHADOW)
                 HANA_SETUP_CASE(HANA_SHADER_BLINN)
@@ -726,13 +755,13 @@ static int run_pass(hana_ctx* ctx, const PassDesc& d) {
                 HANA_SETUP_CASE(HANA_SHADER_TEXTURE_LIGHT)
             }
 #undef HANA_SETUP_CASE
-            prof_end(ctx, PROF_SETUP, ea, eb);
+            prof_end(ctx, PROF_SETUP, ea, eb, st);
             ctx->launches++;
             CU_TRY(cudaGetLastError());
         }
-        prof_begin(ctx, PROF_SCAN, &ea, &eb);
-        scan_kernel<<<d.n_frames, SCAN_THREADS, 0, ctx->stream>>>(p);
-        prof_end(ctx, PROF_SCAN, ea, eb);
+        prof_begin(ctx, PROF_SCAN, &ea, &eb, st);
+        scan_kernel<<<d.n_frames, SCAN_THREADS, 0, st>>>(p);
+        prof_end(ctx, PROF_SCAN, ea, eb, st);
         ctx->launches++;
         CU_TRY(cudaGetLastError());
         if (d.lazy) { /* no read-back: run with what we have, the sweep verifies afterwards */
@@ -742,17 +771,17 @@ static int run_pass(hana_ctx* ctx, const PassDesc& d) {
             c.pool_used = 1;
             c.n_work = 0xFFFFFFFFu;
             if (d.counters_pinned)
-                CU_TRY(cudaMemcpyAsync(d.counters_pinned, sc.counters, sizeof(PassCounters), cudaMemcpyDeviceToHost, ctx->stream));
+                CU_TRY(cudaMemcpyAsync(d.counters_pinned, sc.counters, sizeof(PassCounters), cudaMemcpyDeviceToHost, st));
             if (d.tri_counts_pinned)
                 CU_TRY(cudaMemcpyAsync(d.tri_counts_pinned, sc.tri_count, sizeof(uint32_t) * d.n_frames, cudaMemcpyDeviceToHost,
-                                       ctx->stream));
+                                       st));
             if (d.tri_cap_used) *d.tri_cap_used = tri_cap;
             if (d.pool_cap_used) *d.pool_cap_used = p.pool_cap;
             lists_ready = true;
             break;
         }
-        CU_TRY(cudaMemcpyAsync(sc.counters_host, sc.counters, sizeof(PassCounters), cudaMemcpyDeviceToHost, ctx->stream));
-        CU_TRY(cudaStreamSynchronize(ctx->stream));
+        CU_TRY(cudaMemcpyAsync(sc.counters_host, sc.counters, sizeof(PassCounters), cudaMemcpyDeviceToHost, st));
+        CU_TRY(cudaStreamSynchronize(st));
         const PassCounters& c = *sc.counters_host;
         if (c.tri_needed > tri_cap) {
             if (d.dbg_v2f) return fail(HANA_E_OVERFLOW, "stage output capacity too small: " + std::to_string(c.tri_needed));
@@ -773,21 +802,25 @@ static int run_pass(hana_ctx* ctx, const PassDesc& d) {
     if (d.tri_counts_out && !d.lazy) {
         d.tri_counts_out->resize(d.n_frames);
         CU_TRY(cudaMemcpyAsync(d.tri_counts_out->data(), sc.tri_count, sizeof(uint32_t) * d.n_frames, cudaMemcpyDeviceToHost,
-                               ctx->stream));
-        CU_TRY(cudaStreamSynchronize(ctx->stream));
+                               st));
+        CU_TRY(cudaStreamSynchronize(st));
     }
     if (d.setup_only) return HANA_OK;
 
     cudaEvent_t ea, eb;
-    if (cnt.pool_used > 0) {
+    if (cnt.pool_used > 0 && d.phase != 2) {
         dim3 grid((std::min(cnt.tri_needed, tri_cap) + 255) / 256, d.n_frames);
         if (grid.x > 0) {
-            prof_begin(ctx, PROF_FILL, &ea, &eb);
-            fill_kernel<<<grid, 256, 0, ctx->stream>>>(p);
-            prof_end(ctx, PROF_FILL, ea, eb);
+            prof_begin(ctx, PROF_FILL, &ea, &eb, st);
+            fill_kernel<<<grid, 256, 0, st>>>(p);
+            prof_end(ctx, PROF_FILL, ea, eb, st);
             ctx->launches++;
             CU_TRY(cudaGetLastError());
         }
+    }
+    if (d.phase == 1) {
+        sc.saved_p = p;
+        return HANA_OK;
     }
     if (d.mode == MODE_RMW && cnt.n_work == 0) return HANA_OK; /* nothing covers anything */
 
@@ -824,11 +857,11 @@ static int run_pass(hana_ctx* ctx, const PassDesc& d) {
     const CUtensorMap& ta = d.tm_color ? *d.tm_color : dummy;
     const CUtensorMap& tb = d.tm_depth ? *d.tm_depth : dummy;
     const CUtensorMap& tc = d.tm_r8 ? *d.tm_r8 : dummy;
-    prof_begin(ctx, d.prof_kind, &ea, &eb);
-    int r = d.mode == MODE_CLEAR_FOLD ? launch_raster<MODE_CLEAR_FOLD>(ctx, d.shader, blocks, rp, ta, tb, tc)
-            : d.mode == MODE_RMW      ? launch_raster<MODE_RMW>(ctx, d.shader, blocks, rp, ta, tb, tc)
-                                      : launch_raster<MODE_SHADOW_R8>(ctx, HANA_SHADER_SHADOW, blocks, rp, ta, tb, tc);
-    prof_end(ctx, d.prof_kind, ea, eb);
+    prof_begin(ctx, d.prof_kind, &ea, &eb, st);
+    int r = d.mode == MODE_CLEAR_FOLD ? launch_raster<MODE_CLEAR_FOLD>(st, d.shader, blocks, rp, ta, tb, tc)
+            : d.mode == MODE_RMW      ? launch_raster<MODE_RMW>(st, d.shader, blocks, rp, ta, tb, tc)
+                                      : launch_raster<MODE_SHADOW_R8>(st, HANA_SHADER_SHADOW, blocks, rp, ta, tb, tc);
+    prof_end(ctx, d.prof_kind, ea, eb, st);
     HANA_TRY(r);
     ctx->launches++;
     CU_TRY(cudaGetLastError());
@@ -1049,6 +1082,7 @@ static int sweep_render_passes(hana_sweep* s, const hana_model* model, int shade
     hana_ctx* ctx = s->ctx;
     PassCounters cnt[2];
     memset(cnt, 0, sizeof(cnt));
+    PassDesc shadow_desc;
     if (enable_shadow) { /* scene.h:73-88, into the internal R8 maps */
         PassDesc d;
         d.shader = HANA_SHADER_SHADOW;
@@ -1073,7 +1107,13 @@ static int sweep_render_passes(hana_sweep* s, const hana_model* model, int shade
         d.counters_pinned = &s->pin->counters[0];
         d.tri_cap_used = &s->pending.tri_cap;
         d.pool_cap_used = &s->pending.pool_cap;
+        if (lazy) { /* fork: the main pass is binned on the side stream while this one is binned here */
+            CU_TRY(cudaEventRecord(ctx->ev_fork, ctx->stream));
+            CU_TRY(cudaStreamWaitEvent(ctx->side_stream, ctx->ev_fork, 0));
+            d.phase = 1;
+        }
         HANA_TRY(run_pass(ctx, d));
+        shadow_desc = d;
     }
     PassDesc d;
     d.shader = shader_id;
@@ -1112,7 +1152,21 @@ static int sweep_render_passes(hana_sweep* s, const hana_model* model, int shade
     uint32_t tc = 0, pc = 0;
     d.tri_cap_used = &tc;
     d.pool_cap_used = &pc;
-    HANA_TRY(run_pass(ctx, d));
+    if (lazy && enable_shadow) {
+        d.phase = 1;
+        d.scratch = 1;
+        d.stream = ctx->side_stream;
+        HANA_TRY(run_pass(ctx, d));
+        CU_TRY(cudaEventRecord(ctx->ev_join, ctx->side_stream));
+        shadow_desc.phase = 2;
+        HANA_TRY(run_pass(ctx, shadow_desc)); /* shadow rasteriser */
+        CU_TRY(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
+        d.phase = 2;
+        d.stream = nullptr;
+        HANA_TRY(run_pass(ctx, d));           /* main rasteriser */
+    } else {
+        HANA_TRY(run_pass(ctx, d));
+    }
     if (lazy) { /* the smaller of the two passes' capacities is what both must fit */
         if (!enable_shadow || tc < s->pending.tri_cap) s->pending.tri_cap = tc;
         if (!enable_shadow || pc < s->pending.pool_cap) s->pending.pool_cap = pc;
@@ -1143,8 +1197,9 @@ static int sweep_verify(hana_sweep* s) {
     s->last_stats.tiles_touched = s->pin->counters[1].tiles_touched;
     if (need.tri_needed <= pd.tri_cap && need.pool_needed <= pd.pool_cap) return HANA_OK;
     ctx->tri_cap_hint = std::max(ctx->tri_cap_hint, need.tri_needed + need.tri_needed / 8 + 64);
-    if ((size_t)need.pool_needed > ctx->sc.pool_cap / 4) /* headroom for the other frames of an orbit */
-        HANA_TRY(grow(&ctx->sc.tile_recs, &ctx->sc.pool_cap, ((size_t)need.pool_needed + need.pool_needed / 4) * 4, ctx));
+    for (Scratch* sp : {&ctx->sc, &ctx->sc2}) /* headroom for the other frames of an orbit */
+        if ((size_t)need.pool_needed > sp->pool_cap / 4 && (sp == &ctx->sc || sp->tile_recs))
+            HANA_TRY(grow(&sp->tile_recs, &sp->pool_cap, ((size_t)need.pool_needed + need.pool_needed / 4) * 4, ctx));
     return sweep_render_passes(s, pd.model, pd.shader, pd.enable_shadow, pd.n_frames, pd.diffuse, pd.normal, pd.clear_rgba,
                                pd.clear_depth, false);
 }
