@@ -438,8 +438,9 @@ struct alignas(128) WarpTile {
     uint32_t color[MODE == MODE_SHADOW_R8 ? 32 : TILE_PIX]; /* box 16x16 u32 */
     float depth[MODE == MODE_SHADOW_R8 ? 32 : TILE_PIX];
     uint8_t r8[MODE == MODE_SHADOW_R8 ? TILE_PIX : 128];    /* box 16x16 u8 */
-    uint32_t ord[TILE_PIX];                                 /* winning list ordinal per pixel, parked for shading */
+    uint32_t ord[MODE == MODE_SHADOW_R8 ? 32 : TILE_PIX];   /* winning list ordinal per pixel, parked for shading */
     float4 tri[RW_CHUNK * 4];                               /* staged raster records */
+    float4 sattr[MODE == MODE_SHADOW_R8 ? RW_CHUNK * 2 : 1]; /* SHADOW_R8: their (1/w, clip z) blocks */
     FragUniforms fu;                                        /* the tile's frame: what fragment() reads */
     alignas(8) uint64_t bar;
 };
@@ -561,6 +562,10 @@ __global__ void __launch_bounds__(RW_THREADS, ShaderAttrs<SHADER>::LIT ? 6 : 7)
                   const __grid_constant__ CUtensorMap tm_r8) {
     constexpr int NQ = ShaderAttrs<SHADER>::NQ;
     constexpr unsigned FULL = 0xFFFFFFFFu;
+    /* SHADOW_R8 (always the ShadowShader): its one-attribute fragment() is evaluated right where a fragment wins the
+     * resolve and the byte rides in the top 8 bits of the state word, so nothing is parked or re-fetched afterwards */
+    constexpr bool INLOOP = (MODE == MODE_SHADOW_R8);
+    constexpr uint32_t ORD_MASK = INLOOP ? 0x00FFFFFFu : 0xFFFFFFFFu;
     __shared__ RasterSmem<MODE> sm;
     const PassParams& p = q.p;
     const unsigned lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
@@ -663,6 +668,11 @@ __global__ void __launch_bounds__(RW_THREADS, ShaderAttrs<SHADER>::LIT ? 6 : 7)
             if ((int)lane < n) {
                 const float4 b = __ldg(list + ((size_t)c0 + lane) * 4 + 2);
                 mask = subblock_mask(__float_as_uint(b.x), __float_as_uint(b.y), X0, Y0);
+                if (INLOOP) {
+                    const float4* ap = p.tri_attr + ((size_t)f * p.tri_cap + __float_as_uint(b.z)) * 2;
+                    wt.sattr[lane * 2] = __ldg(ap);
+                    wt.sattr[lane * 2 + 1] = __ldg(ap + 1);
+                }
             }
             __syncwarp();
             for (int j = 0; j < n; j++) {
@@ -694,13 +704,21 @@ __global__ void __launch_bounds__(RW_THREADS, ShaderAttrs<SHADER>::LIT ? 6 : 7)
                                 } else {
                                     win = z < bz[sb];
                                     if (z == bz[sb]) { /* rare: equal depths, the later submission wins */
-                                        const uint32_t kb = __float_as_uint(__ldg(list + (size_t)bj[sb] * 4 + 2).w);
+                                        const uint32_t kb = __float_as_uint(__ldg(list + (size_t)(bj[sb] & ORD_MASK) * 4 + 2).w);
                                         win = __float_as_uint(r2.w) > kb;
                                     }
                                 }
                                 if (win) {
                                     bz[sb] = z;
                                     bj[sb] = c0 + (uint32_t)j;
+                                    if (INLOOP) { /* ShadowShader::fragment IShader.cpp:176-180 on the winning fragment */
+                                        const float4 rw = wt.sattr[j * 2], a = wt.sattr[j * 2 + 1];
+                                        const VaryingWeights vw = varying_weights(w0, w1, w2, rw.x, rw.y, rw.z);
+                                        const float attr0 = interp(vw, a.x, a.y, a.z);
+                                        float rgb[3];
+                                        fragment_shader<HANA_SHADER_SHADOW>(wt.fu, &attr0, q.diffuse, q.normal, q.shadow, rgb);
+                                        bj[sb] |= (colour_bytes(rgb) & 255u) << 24;
+                                    }
                                 }
                             }
                         }
@@ -709,18 +727,33 @@ __global__ void __launch_bounds__(RW_THREADS, ShaderAttrs<SHADER>::LIT ? 6 : 7)
             }
         }
 
-        /* -- park the resolve state, shade the winners one sub-block at a time (graphics.cpp:362-373) -- */
         if (tma && MODE != MODE_RMW) {
             if (lane == 0) tma_wait_read0(); /* the previous tile's stores have drained the staging tile */
             __syncwarp();
         }
+        uint32_t covered_acc = 0;
+        if (INLOOP) {
+#pragma unroll
+            for (int sb = 0; sb < 8; sb++) {
+                const int pix = ((sb >> 1) * 4 + ly) * TILE + (sb & 1) * 8 + lx;
+                const uint8_t v = (uint8_t)(bj[sb] == ORD_NONE ? 0u : (bj[sb] >> 24));
+                if (q.pixels_covered) covered_acc += __popc(__ballot_sync(FULL, bj[sb] != ORD_NONE));
+                if (tma) {
+                    wt.r8[pix] = v;
+                } else {
+                    const int px = ipx0 + (sb & 1) * 8, py = ipy0 + (sb >> 1) * 4;
+                    if (px < p.W && py < p.H)
+                        q.shadow_out[(size_t)f * q.shadow_out_frame_stride + (size_t)py * q.shadow_out_pitch + px] = v;
+                }
+            }
+        } else {
+        /* -- park the resolve state, shade the winners one sub-block at a time (graphics.cpp:362-373) -- */
 #pragma unroll
         for (int sb = 0; sb < 8; sb++) {
             const int pix = ((sb >> 1) * 4 + ly) * TILE + (sb & 1) * 8 + lx;
             wt.ord[pix] = bj[sb];
-            if (MODE != MODE_SHADOW_R8) wt.depth[pix] = bz[sb];
+            wt.depth[pix] = bz[sb];
         }
-        uint32_t covered_acc = 0;
         DevShadow sh = q.shadow;
         if (sh.base) sh.base += (size_t)f * q.shadow_frame_stride;
 #pragma unroll 1
@@ -748,18 +781,15 @@ __global__ void __launch_bounds__(RW_THREADS, ShaderAttrs<SHADER>::LIT ? 6 : 7)
             }
             if (q.pixels_covered) covered_acc += __popc(__ballot_sync(FULL, j != ORD_NONE));
             if (tma) {
-                if (MODE == MODE_SHADOW_R8) wt.r8[pix] = (uint8_t)(j != ORD_NONE ? (col & 255u) : 0u);
-                else wt.color[pix] = col;
+                wt.color[pix] = col;
             } else if (in_frame) {
-                if (MODE == MODE_SHADOW_R8) {
-                    q.shadow_out[(size_t)f * q.shadow_out_frame_stride + (size_t)py * q.shadow_out_pitch + px] =
-                        (uint8_t)(j != ORD_NONE ? (col & 255u) : 0u);
-                } else if (MODE == MODE_CLEAR_FOLD || j != ORD_NONE) {
+                if (MODE == MODE_CLEAR_FOLD || j != ORD_NONE) {
                     const size_t o = (size_t)f * q.frame_stride + (size_t)py * p.W + px;
                     q.color[o] = col;
                     q.depth[o] = wt.depth[pix];
                 }
             }
+        }
         }
         if (q.pixels_covered && lane == 0 && covered_acc) atomicAdd(q.pixels_covered + f, covered_acc);
 
