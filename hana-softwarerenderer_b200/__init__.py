@@ -30,6 +30,11 @@ from .api import (  # noqa: F401
     device_count,
     lib_path,
     load,
+    obj_load,
+    tga_load,
+    tga_write,
+    PRESENT_BGRA8,
+    PRESENT_BGR8,
 )
 from . import scene, sharding  # noqa: F401
 from .scene import (  # noqa: F401

@@ -131,6 +131,10 @@ def load():
         "hana_sweep_device_ptrs": [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(C.c_size_t)],
         "hana_sweep_checksums": [vp, i, vp],
         "hana_sweep_stats": [vp, i, vp],
+        "hana_sweep_present": [vp, i, i, i, vp, C.POINTER(vp)],
+        "hana_tga_write": [C.c_char_p, vp, i, i, i, i],
+        "hana_obj_load": [C.c_char_p, i, C.POINTER(vp), C.POINTER(i)],
+        "hana_tga_load": [C.c_char_p, i, C.POINTER(vp), C.POINTER(i), C.POINTER(i), C.POINTER(i)],
         "hana_host_alloc": [C.c_size_t, C.POINTER(vp)],
         "hana_host_free": [vp],
         "hana_stage_vertex": [vp, vp, i, vp, vp],
@@ -141,6 +145,8 @@ def load():
         fn = getattr(L, name)
         fn.argtypes = args
         fn.restype = C.c_int
+    L.hana_free.argtypes = [vp]
+    L.hana_free.restype = None
     _LIB = L
     return L
 
@@ -400,6 +406,14 @@ class Sweep:
         _ck(self.ctx.L.hana_sweep_download_async(self.h, first, count, C.c_void_p(color_ptr),
                                                  C.c_void_p(depth_ptr) if depth_ptr else None))
 
+    def present(self, first, count, fmt=0):
+        """window_draw_buffer's surface (win32.cpp:348-370) of frames [first, first+count): top-down B,G,R,255 (fmt 0)
+        or B,G,R (fmt 1), converted on the device."""
+        out = np.empty((count, self.height, self.width, 4 if fmt == 0 else 3), np.uint8)
+        _ck(self.ctx.L.hana_sweep_present(self.h, first, count, fmt, _ptr(out), None))
+        self.ctx.sync()
+        return out
+
     def checksums(self, n_frames):
         out = np.zeros(n_frames, np.uint64)
         _ck(self.ctx.L.hana_sweep_checksums(self.h, n_frames, _ptr(out)))
@@ -430,6 +444,43 @@ def frame_checksum(color, depth):
         v = (rgb << np.uint64(32)) | d
         idx = np.arange(v.size, dtype=np.uint64) + np.uint64(0x9E3779B97F4A7C15)
         return np.uint64(np.sum(mix(v ^ mix(idx)), dtype=np.uint64))
+
+
+PRESENT_BGRA8, PRESENT_BGR8 = 0, 1
+
+
+def obj_load(path, normal_pass=1):
+    """OBJ -> (ncorners, 8) float32 a2v stream; no GPU needed."""
+    L = load()
+    p, n = C.c_void_p(), C.c_int()
+    _ck(L.hana_obj_load(os.fsencode(path), int(normal_pass), C.byref(p), C.byref(n)))
+    try:
+        a = np.ctypeslib.as_array((C.c_float * (n.value * 8)).from_address(p.value)).reshape(n.value, 8).copy() if n.value else \
+            np.zeros((0, 8), np.float32)
+    finally:
+        L.hana_free(p)
+    return a
+
+
+def tga_load(path, model_flip=True):
+    """TGA -> (h, w, bytespp) uint8 as Model holds it (model_flip) or as TGAImage::read_tga_file leaves it."""
+    L = load()
+    p, w, h, b = C.c_void_p(), C.c_int(), C.c_int(), C.c_int()
+    _ck(L.hana_tga_load(os.fsencode(path), int(bool(model_flip)), C.byref(p), C.byref(w), C.byref(h), C.byref(b)))
+    try:
+        n = w.value * h.value * b.value
+        a = np.ctypeslib.as_array((C.c_uint8 * n).from_address(p.value)).reshape(h.value, w.value, b.value).copy()
+    finally:
+        L.hana_free(p)
+    return a
+
+
+def tga_write(path, data, rle=False):
+    """(h, w, bytespp) uint8, rows in file order -> TGA file (tgaimage.cpp:145-246 byte for byte)."""
+    a = np.ascontiguousarray(data, np.uint8)
+    if a.ndim == 2:
+        a = a[:, :, None]
+    _ck(load().hana_tga_write(os.fsencode(path), _ptr(a), a.shape[1], a.shape[0], a.shape[2], int(bool(rle))))
 
 
 class PinnedBuffer:

@@ -31,6 +31,7 @@ static int fail(int code, const std::string& msg) {
     g_err = msg;
     return code;
 }
+extern "C" int hana_set_error(int code, const char* msg) { return fail(code, msg ? msg : ""); } /* for host/ sources */
 #define CU_TRY(expr)                                                                                             \
     do {                                                                                                         \
         cudaError_t e__ = (expr);                                                                                \
@@ -152,6 +153,8 @@ struct hana_sweep {
     uint32_t* tri_counts_pin;      /* pinned host: [2][max_frames] */
     cudaEvent_t ev_render, ev_copy;
     bool copy_in_flight;
+    uint8_t* present_buf;          /* device: presented frames (hana_sweep_present) */
+    size_t present_cap;
     struct Pending {
         bool active = false;
         const hana_model* model = nullptr;
@@ -1024,7 +1027,7 @@ extern "C" int hana_sweep_create(hana_ctx* ctx, int width, int height, int max_f
     s->shadow_frame_bytes = (size_t)s->shadow_pitch * ((height + 15) / 16 * 16);
     s->color = nullptr; s->depth = nullptr; s->shadow_r8 = nullptr; s->u_raw = nullptr; s->u_dev = nullptr;
     s->checksums = nullptr; s->pix_counts = nullptr; s->overflow = nullptr; s->pin = nullptr; s->tri_counts_pin = nullptr;
-    s->ev_render = nullptr; s->ev_copy = nullptr; s->copy_in_flight = false;
+    s->ev_render = nullptr; s->ev_copy = nullptr; s->copy_in_flight = false; s->present_buf = nullptr; s->present_cap = 0;
     cudaError_t e = cudaMalloc(&s->color, n * 4 * max_frames);
     if (e == cudaSuccess) e = cudaMalloc(&s->depth, n * 4 * max_frames);
     if (e == cudaSuccess) e = cudaMalloc(&s->shadow_r8, s->shadow_frame_bytes * max_frames);
@@ -1064,7 +1067,7 @@ extern "C" int hana_sweep_destroy(hana_sweep* s) {
     cudaStreamSynchronize(ctx->stream);
     cudaStreamSynchronize(ctx->copy_stream);
     cudaFree(s->color); cudaFree(s->depth); cudaFree(s->shadow_r8); cudaFree(s->u_raw); cudaFree(s->u_dev);
-    cudaFree(s->checksums); cudaFree(s->pix_counts); cudaFree(s->overflow);
+    cudaFree(s->checksums); cudaFree(s->pix_counts); cudaFree(s->overflow); cudaFree(s->present_buf);
     if (s->pin) cudaFreeHost(s->pin);
     if (s->tri_counts_pin) cudaFreeHost(s->tri_counts_pin);
     if (s->ev_render) cudaEventDestroy(s->ev_render);
@@ -1297,6 +1300,47 @@ extern "C" int hana_sweep_download_async(hana_sweep* s, int first, int count, ui
         CU_TRY(cudaMemcpyAsync(depth_pinned, s->depth + n * first, n * 4 * count, cudaMemcpyDeviceToHost, ctx->copy_stream));
     CU_TRY(cudaEventRecord(s->ev_copy, ctx->copy_stream));
     s->copy_in_flight = true;
+    return HANA_OK;
+}
+/* The presentable surface of frames [first, first+count) (win32.cpp:348-370): rows top-down, B,G,R[,255]. The
+ * conversion runs on the device after the sweep's render; the copy to dst_host (pinned for overlap) runs on the copy
+ * stream and is complete after hana_sync(). dst_dev_out (optional) receives the device address of the surfaces. */
+extern "C" int hana_sweep_present(hana_sweep* s, int first, int count, int format, uint8_t* dst_host, void** dst_dev_out) {
+    if (!s) return fail(HANA_E_INVALID, "sweep is NULL");
+    if (first < 0 || count < 1 || first + count > s->max_frames) return fail(HANA_E_INVALID, "frame range out of bounds");
+    if (format != HANA_PRESENT_BGRA8 && format != HANA_PRESENT_BGR8) return fail(HANA_E_INVALID, "unknown present format");
+    hana_ctx* ctx = s->ctx;
+    HANA_TRY(use_device(ctx));
+    HANA_TRY(sweep_verify(s));
+    const size_t bytes = (size_t)s->w * s->h * (format == HANA_PRESENT_BGRA8 ? 4 : 3) * count;
+    if (s->copy_in_flight) { /* the previous copy reads present_buf / the ring */
+        CU_TRY(cudaStreamWaitEvent(ctx->stream, s->ev_copy, 0));
+        s->copy_in_flight = false;
+    }
+    if (bytes > s->present_cap) {
+        CU_TRY(cudaStreamSynchronize(ctx->stream));
+        CU_TRY(cudaStreamSynchronize(ctx->copy_stream));
+        cudaFree(s->present_buf);
+        s->present_buf = nullptr;
+        s->present_cap = 0;
+        CU_TRY(cudaMalloc(&s->present_buf, bytes));
+        s->present_cap = bytes;
+    }
+    dim3 grid((unsigned)((s->w + 1023) / 1024), (unsigned)s->h, (unsigned)count);
+    cudaEvent_t a, b;
+    prof_begin(ctx, PROF_OTHER, &a, &b);
+    present_kernel<<<grid, 256, 0, ctx->stream>>>(s->color, (size_t)s->w * s->h, first, s->w, s->h, format, s->present_buf);
+    prof_end(ctx, PROF_OTHER, a, b);
+    ctx->launches++;
+    CU_TRY(cudaGetLastError());
+    if (dst_dev_out) *dst_dev_out = s->present_buf;
+    if (dst_host) {
+        CU_TRY(cudaEventRecord(s->ev_render, ctx->stream));
+        CU_TRY(cudaStreamWaitEvent(ctx->copy_stream, s->ev_render, 0));
+        CU_TRY(cudaMemcpyAsync(dst_host, s->present_buf, bytes, cudaMemcpyDeviceToHost, ctx->copy_stream));
+        CU_TRY(cudaEventRecord(s->ev_copy, ctx->copy_stream));
+        s->copy_in_flight = true;
+    }
     return HANA_OK;
 }
 extern "C" int hana_sweep_device_ptrs(hana_sweep* s, void** color_dev, void** depth_dev, size_t* frame_stride_pixels) {

@@ -842,6 +842,49 @@ __global__ void fill32_kernel(uint32_t* __restrict__ dst, uint32_t value, size_t
     for (size_t k = n4 * 4 + i; k < n; k += stride) dst[k] = value;
 }
 
+/* ---- present ------------------------------------------------------
+ * window_draw_buffer win32.cpp:348-370: row r of the render buffer (y up) lands in row H-1-r of the surface and R, B
+ * change places. format 0: 4 bytes per pixel B,G,R,255; format 1: 3 bytes per pixel B,G,R (a TGA payload, rows
+ * top-down as tgaimage.cpp:166 flags them). One thread per 4 pixels of a row: 128-bit loads, 128- or 3x32-bit stores. */
+__global__ void __launch_bounds__(256) present_kernel(const uint32_t* __restrict__ color, size_t frame_stride, int first,
+                                                      int W, int H, int format, uint8_t* __restrict__ dst) {
+    const int f = blockIdx.z;
+    const int y = blockIdx.y;
+    const int x4 = (blockIdx.x * 256 + threadIdx.x) * 4;
+    if (x4 >= W) return;
+    const uint32_t* src = color + (size_t)(first + f) * frame_stride + (size_t)y * W + x4;
+    const int bpp = format == 0 ? 4 : 3;
+    uint8_t* out = dst + ((size_t)f * H + (size_t)(H - 1 - y)) * (size_t)W * bpp + (size_t)x4 * bpp;
+    uint32_t c[4];
+    const int n = min(4, W - x4);
+    if (n == 4 && (W & 3) == 0) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(src));
+        c[0] = v.x; c[1] = v.y; c[2] = v.z; c[3] = v.w;
+    } else {
+        for (int k = 0; k < 4; k++) c[k] = k < n ? __ldg(src + k) : 0u;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; k++) c[k] = ((c[k] >> 16) & 0xFFu) | (c[k] & 0xFF00u) | ((c[k] & 0xFFu) << 16); /* 0x00RRGGBB: B,G,R bytes */
+    if (format == 0) {
+        if (n == 4 && (W & 3) == 0) {
+            *reinterpret_cast<uint4*>(out) = make_uint4(c[0] | 0xFF000000u, c[1] | 0xFF000000u, c[2] | 0xFF000000u, c[3] | 0xFF000000u);
+        } else {
+            for (int k = 0; k < n; k++) reinterpret_cast<uint32_t*>(out)[k] = c[k] | 0xFF000000u;
+        }
+    } else if (n == 4 && (W & 3) == 0) { /* 12 bytes, 4-byte aligned because W*3 is a multiple of 4 */
+        uint32_t* o = reinterpret_cast<uint32_t*>(out);
+        o[0] = c[0] | (c[1] << 24);
+        o[1] = (c[1] >> 8) | (c[2] << 16);
+        o[2] = (c[2] >> 16) | (c[3] << 8);
+    } else {
+        for (int k = 0; k < n; k++) {
+            out[3 * k] = (uint8_t)c[k];
+            out[3 * k + 1] = (uint8_t)(c[k] >> 8);
+            out[3 * k + 2] = (uint8_t)(c[k] >> 16);
+        }
+    }
+}
+
 /* Order-independent 64-bit frame checksum: sum over pixels of mix(index, RGB, depth bits).
  * tests/ and the multi-GPU sharding check recompute it with numpy. */
 __device__ __forceinline__ uint64_t mix64(uint64_t x) {

@@ -248,6 +248,28 @@ HANA_API int hana_sweep_device_ptrs(hana_sweep* s, void** color_dev, void** dept
 HANA_API int hana_sweep_checksums(hana_sweep* s, int n_frames, uint64_t* out_host);
 HANA_API int hana_sweep_stats(hana_sweep* s, int frame, HanaStats* out); /* synchronises */
 
+/* --- present / output ------------------------------------ */
+/* Replaces window_draw_buffer's conversion loop (win32.cpp:348-370): frames [first, first+count) of the last batch
+ * as top-down B,G,R,255 (BGRA8) or B,G,R (BGR8, a TGA payload) surfaces, converted on the device; copied to dst_host
+ * (pinned memory overlaps the next batch; may be NULL) on the copy stream, complete after hana_sync(). */
+#define HANA_PRESENT_BGRA8 0
+#define HANA_PRESENT_BGR8 1
+HANA_API int hana_sweep_present(hana_sweep* s, int first, int count, int format, uint8_t* dst_host, void** dst_dev_out);
+/* Replaces TGAImage::write_tga_file (tgaimage.cpp:145-246): `data` = w*h*bytespp bytes in file order (top-left
+ * origin is flagged); raw or RLE; byte-identical files. */
+HANA_API int hana_tga_write(const char* path, const uint8_t* data, int w, int h, int bytespp, int rle);
+
+/* --- asset ingestion -------------------------------------- */
+/* Replaces Model::Model's OBJ parse + the per-corner gather of graphics.cpp:380-386 (model.cpp:6-48, 66-111):
+ * out_a2v = malloc'd ncorners*8 floats (obj_pos, obj_normal, uv) ready for hana_model_upload; release with hana_free.
+ * normal_pass >= 1: which walk of the reference's draw loop the normals correspond to (Model::normal re-normalises
+ * in place on every access, model.cpp:108-111). */
+HANA_API int hana_obj_load(const char* path, int normal_pass, float** out_a2v, int* out_ncorners);
+/* Replaces TGAImage::read_tga_file (tgaimage.cpp:40-143) and, with model_flip != 0, Model::load_texture's extra
+ * flip (model.cpp:74-84): malloc'd w*h*bytespp bytes ready for hana_texture_upload; release with hana_free. */
+HANA_API int hana_tga_load(const char* path, int model_flip, uint8_t** out_data, int* out_w, int* out_h, int* out_bytespp);
+HANA_API void hana_free(void* p);
+
 /* Pinned host memory helpers for the e2e path. */
 HANA_API int hana_host_alloc(size_t bytes, void** out);
 HANA_API int hana_host_free(void* p);

@@ -190,6 +190,41 @@ def reference_available(instrumented=True):
     return os.path.exists(REF_INST_SO if instrumented else REF_SO)
 
 
+class RefCodecs:
+    """The reference's own OBJ / TGA codecs (model.cpp, tgaimage.cpp) through oracle/ref_driver.cpp."""
+
+    def __init__(self):
+        if not os.path.exists(REF_SO):
+            raise FileNotFoundError(REF_SO + " (run oracle/build_ref.sh where /root/reference exists)")
+        L = self.lib = C.CDLL(REF_SO)
+        L.href_tga_write.argtypes = [C.c_char_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
+        L.href_tga_read.argtypes = [C.c_char_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.href_obj_a2v.argtypes = [C.c_char_p, C.c_int, C.c_void_p, C.c_int]
+
+    def tga_write(self, path, data, rle):
+        a = np.ascontiguousarray(data, np.uint8)
+        if a.ndim == 2:
+            a = a[:, :, None]
+        r = self.lib.href_tga_write(os.fsencode(path), a.ctypes.data_as(C.c_void_p), a.shape[1], a.shape[0], a.shape[2], int(rle))
+        if r != 0:
+            raise RuntimeError("reference write_tga_file failed")
+
+    def tga_read(self, path, model_flip):
+        w, h, b = C.c_int(), C.c_int(), C.c_int()
+        if self.lib.href_tga_read(os.fsencode(path), int(model_flip), None, C.byref(w), C.byref(h), C.byref(b)) != 0:
+            raise RuntimeError("reference read_tga_file failed")
+        out = np.empty((h.value, w.value, b.value), np.uint8)
+        self.lib.href_tga_read(os.fsencode(path), int(model_flip), out.ctypes.data_as(C.c_void_p), C.byref(w), C.byref(h), C.byref(b))
+        return out
+
+    def obj_a2v(self, path, normal_pass):
+        n = self.lib.href_obj_a2v(os.fsencode(path), normal_pass, None, 0)
+        out = np.empty((n, 8), np.float32)
+        if self.lib.href_obj_a2v(os.fsencode(path), normal_pass, out.ctypes.data_as(C.c_void_p), n) != n:
+            raise RuntimeError("reference Model export failed")
+        return out
+
+
 class Reference:
     """The real reference behind oracle/ref_driver.cpp (one scene per instance)."""
 

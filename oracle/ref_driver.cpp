@@ -263,6 +263,43 @@ int href_texture_info(HrefScene* s, int which, int* w, int* h, int* bpp, const u
     return 0;
 }
 
+// --- the reference's own codecs, for the asset / output tests ---
+// TGAImage::write_tga_file (tgaimage.cpp:145) of `data` (rows in file order).
+int href_tga_write(const char* path, const uint8_t* data, int w, int h, int bpp, int rle) {
+    TGAImage img(w, h, bpp);
+    memcpy(img.buffer(), data, (size_t)w * h * bpp);
+    return img.write_tga_file(path, rle != 0) ? 0 : -1;
+}
+// TGAImage::read_tga_file (tgaimage.cpp:40) [+ Model::load_texture's flip_vertically, model.cpp:81].
+// out == NULL: returns the size only.
+int href_tga_read(const char* path, int model_flip, uint8_t* out, int* w, int* h, int* bpp) {
+    TGAImage img;
+    if (!img.read_tga_file(path)) return -1;
+    if (model_flip) img.flip_vertically();
+    *w = img.get_width();
+    *h = img.get_height();
+    *bpp = img.get_bytespp();
+    if (out) memcpy(out, img.buffer(), (size_t)(*w) * (*h) * (*bpp));
+    return 0;
+}
+// A fresh Model (model.cpp:6) walked `pass` times the way graphics.cpp:380-386 walks it; the a2v stream of the last walk.
+int href_obj_a2v(const char* path, int pass, float* out, int capacity_corners) {
+    Model m(path);
+    int n = m.nfaces() * 3;
+    if (!out) return n;
+    if (capacity_corners < n) return -1;
+    for (int k = 1; k <= pass; k++)
+        for (int i = 0; i < m.nfaces(); i++)
+            for (int j = 0; j < 3; j++) {
+                Vector3f p = m.vert(i, j);
+                Vector3f nn = m.normal(i, j);
+                Vector2f t = m.uv(i, j);
+                float* d = out + (size_t)(i * 3 + j) * 8;
+                d[0] = p.x; d[1] = p.y; d[2] = p.z; d[3] = nn.x; d[4] = nn.y; d[5] = nn.z; d[6] = t.x; d[7] = t.y;
+            }
+    return n;
+}
+
 #ifdef HREF_INSTRUMENTED
 void href_counters_reset(void) { memset(&g_cnt, 0, sizeof(g_cnt)); }
 void href_counters_get(uint64_t* out5) {

@@ -1,0 +1,80 @@
+"""The asynchronous sweep contract (include/hana_b200.h): a render returns before the GPU has run it and nothing is
+read back inside it; if the batch ran out of internal scratch (triangle slots, tile-list records) the sweep's next
+synchronising call renders it again with more. Checked by rendering, in ONE context sized by a tiny scene, a scene that
+needs far more of both, and comparing with a context that never saw the tiny scene; and by interleaving two rings."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _scenes(hana):
+    small = hana.synthetic_scene("blob")
+    a2v = hana.scene.synthetic_grid(300, 170, seed=5)          # 101 062 triangles, ~4 px each at 640x360
+    dif, nm = hana.scene.noise_textures(5, 128, flat_normal=True)
+    return small, hana.Scene("grid", a2v, dif, nm)
+
+
+def test_overflowing_batch_is_rendered_again(hana):
+    W, Hh, F = 640, 360, 3
+    small, big = _scenes(hana)
+    us = [hana.default_uniforms(W, Hh, True) for _ in range(F)]
+
+    fresh = hana.Context(0)
+    objs = big.upload(fresh)
+    sw = fresh.sweep(W, Hh, F)
+    sw.render(objs[0], hana.BLINN, us, objs[1], objs[2])
+    want = sw.checksums(F)
+    want_frame = sw.download(1)
+    for o in (sw,) + tuple(objs):
+        o.close()
+    fresh.close()
+
+    ctx = hana.Context(0)
+    s_objs = small.upload(ctx)
+    sw = ctx.sweep(W, Hh, F)
+    sw.render(s_objs[0], hana.BLINN, us, s_objs[1], s_objs[2])   # sizes the scratch for ~1e3 triangles
+    sw.checksums(F)
+    b_objs = big.upload(ctx)
+    sw.render(b_objs[0], hana.BLINN, us, b_objs[1], b_objs[2])   # needs 100x that: dropped, then re-rendered
+    got = sw.checksums(F)
+    assert np.array_equal(got, want)
+    col, dep = sw.download(1)
+    assert np.array_equal(col[..., :3], want_frame[0][..., :3]) and np.array_equal(dep.view(np.uint32), want_frame[1].view(np.uint32))
+    st = sw.stats(1)
+    assert st["faces_in"] == big.nfaces and st["tris_out"] > 1000
+    # steady state: the same batch again must not need the second attempt and gives the same frames
+    sw.render(b_objs[0], hana.BLINN, us, b_objs[1], b_objs[2])
+    assert np.array_equal(sw.checksums(F), want)
+    for o in (sw,) + tuple(s_objs) + tuple(b_objs):
+        o.close()
+    ctx.close()
+
+
+def test_two_rings_with_overlapped_copies(hana, ctx):
+    """Render into ring A, start its copy, render into ring B while the copy runs: both arrive intact."""
+    W, Hh, F = 320, 240, 4
+    scene = hana.synthetic_scene("blob")
+    model, dtex, ntex = scene.upload(ctx)
+    rings = [ctx.sweep(W, Hh, F), ctx.sweep(W, Hh, F)]
+    pins = [hana.api.PinnedBuffer(W * Hh * 4 * F) for _ in range(2)]
+    batches = [hana.orbit_sweep_uniforms(W, Hh, 16 * k, F, frames_per_turn=64) for k in range(4)]
+    want = []
+    for b in batches:
+        rings[0].render(model, hana.BLINN, b, dtex, ntex)
+        want.append(np.stack([rings[0].download(k)[0] for k in range(F)]))
+    got = []
+    for k, b in enumerate(batches):
+        r = rings[k & 1]
+        if k >= 2:                                           # the copy of batch k-2 used this pinned buffer
+            ctx.sync()
+            got.append(np.frombuffer(pins[k & 1].array, np.uint8).reshape(F, Hh, W, 4).copy())
+        r.render(model, hana.BLINN, b, dtex, ntex)
+        r.download_async(0, F, pins[k & 1].ptr, None)
+    ctx.sync()
+    got.append(np.frombuffer(pins[0].array, np.uint8).reshape(F, Hh, W, 4).copy())
+    got.append(np.frombuffer(pins[1].array, np.uint8).reshape(F, Hh, W, 4).copy())
+    for k in range(4):
+        assert np.array_equal(got[k], want[k]), k
+    for o in rings + [model, dtex, ntex] + pins:
+        o.close()
