@@ -9,3 +9,4 @@ for n in ('bench_v3',):
     d=json.load(open('gpurun_out/%s.json'%n))
     print(n, d['value'], d['us_per_frame'], 'e2e', d['e2e']['value'], d['e2e_color_depth']['value'], d['kernel_ms_per_step'], d['roofline']['frac'], d['frame_roofline']['frac'], 'ms/step', d['ms_per_step'])
 PY
+timeout 900 python tools/time_configs.py 2>&1 | tail -2 | tee gpurun_out/configs_time.jsonl | cut -c1-700

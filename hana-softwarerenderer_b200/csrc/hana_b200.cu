@@ -763,7 +763,7 @@ static int run_pass(hana_ctx* ctx, const PassDesc& d) {
             CU_TRY(cudaGetLastError());
         }
         prof_begin(ctx, PROF_SCAN, &ea, &eb, st);
-        scan_kernel<<<d.n_frames, SCAN_THREADS, 0, st>>>(p);
+        scan_kernel<<<dim3((unsigned)((n_tiles + SCAN_CHUNK - 1) / SCAN_CHUNK), (unsigned)d.n_frames), SCAN_THREADS, 0, st>>>(p);
         prof_end(ctx, PROF_SCAN, ea, eb, st);
         ctx->launches++;
         CU_TRY(cudaGetLastError());

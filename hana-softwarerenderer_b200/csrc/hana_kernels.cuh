@@ -35,7 +35,7 @@ constexpr int TILE_PIX = TILE * TILE;
 constexpr int TILE_BITS = 20;        /* work item = frame << 20 | tile_y << 10 | tile_x */
 constexpr uint32_t TILE_MASK = (1u << TILE_BITS) - 1u;
 constexpr uint32_t WORK_INVALID = 0xFFFFFFFFu;
-constexpr int SETUP_THREADS = 128;
+constexpr int SETUP_THREADS = 256;
 constexpr int SCAN_THREADS = 1024;
 
 enum RasterMode {
@@ -265,25 +265,35 @@ __global__ void __launch_bounds__(SETUP_THREADS) setup_kernel(PassParams p) {
             setup_clipped<SHADER>(p, f, face, v);
         }
     }
-    /* warp-shuffle prefix sum over the emit flags -> one atomic per warp */
-    unsigned ballot = __ballot_sync(0xFFFFFFFFu, emit);
-    if (ballot) {
-        int incl = emit ? 1 : 0;
+    /* shuffle prefix sum over the emit flags per warp, warp totals combined in shared memory -> ONE slot-allocation
+     * atomic per CTA (a dense mesh has millions of faces per frame, all allocating from the same counter) */
+    __shared__ uint32_t s_warp_total[SETUP_THREADS / 32];
+    __shared__ uint32_t s_cta_base;
+    const unsigned wid = threadIdx.x >> 5;
+    int incl = emit ? 1 : 0;
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            int t = __shfl_up_sync(0xFFFFFFFFu, incl, d);
-            if ((int)lane >= d) incl += t;
+    for (int d = 1; d < 32; d <<= 1) {
+        int t = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+        if ((int)lane >= d) incl += t;
+    }
+    if (lane == 31) s_warp_total[wid] = (uint32_t)incl;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t total = 0;
+#pragma unroll
+        for (int w = 0; w < SETUP_THREADS / 32; w++) {
+            const uint32_t t = s_warp_total[w];
+            s_warp_total[w] = total; /* exclusive */
+            total += t;
         }
-        int total = __shfl_sync(0xFFFFFFFFu, incl, 31);
-        uint32_t base = 0;
-        if (lane == 0) base = atomicAdd(p.tri_count + f, (uint32_t)total);
-        base = __shfl_sync(0xFFFFFFFFu, base, 0);
-        if (emit) {
-            uint32_t slot = base + (uint32_t)(incl - 1);
-            if (slot < p.tri_cap) {
-                store_triangle<SHADER>(p, f, slot, r, v, v + V2F_N, v + 2 * V2F_N);
-                count_tiles(p, f, r);
-            }
+        s_cta_base = total ? atomicAdd(p.tri_count + f, total) : 0u;
+    }
+    __syncthreads();
+    if (emit) {
+        const uint32_t slot = s_cta_base + s_warp_total[wid] + (uint32_t)(incl - 1);
+        if (slot < p.tri_cap) {
+            store_triangle<SHADER>(p, f, slot, r, v, v + V2F_N, v + 2 * V2F_N);
+            count_tiles(p, f, r);
         }
     }
 }
@@ -316,44 +326,48 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t val, uint32_t*
     return r;
 }
 
+/* One CTA per chunk of SCAN_CHUNK consecutive tiles of a frame (4 per thread): chunk totals by a block scan, ONE
+ * reservation of pool records and of work-queue entries per chunk, then the offsets. Lists need no particular order
+ * in the pool and the queue none among its entries, so chunks do not wait for each other. */
+constexpr int SCAN_CHUNK = SCAN_THREADS * 4;
 __global__ void __launch_bounds__(SCAN_THREADS) scan_kernel(PassParams p) {
     __shared__ uint32_t warp_sums[32];
     __shared__ uint32_t s_total_refs, s_total_ne, s_base_refs, s_base_work;
-    const int f = blockIdx.x;
-    const int per = (p.n_tiles + SCAN_THREADS - 1) / SCAN_THREADS;
-    const int t0 = threadIdx.x * per;
-    const int t1 = min(t0 + per, p.n_tiles);
+    const int f = blockIdx.y;
+    const int t0 = blockIdx.x * SCAN_CHUNK + (int)threadIdx.x * 4;
     const uint32_t* tc = p.tile_count + (size_t)f * p.n_tiles;
-    uint32_t refs = 0, ne = 0;
-    for (int t = t0; t < t1; t++) {
-        uint32_t c = tc[t];
-        refs += c;
-        ne += (c != 0u);
-    }
-    uint32_t ex_refs = block_exclusive_scan(refs, &s_total_refs, warp_sums);
-    uint32_t ex_ne = block_exclusive_scan(ne, &s_total_ne, warp_sums);
+    uint32_t c[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) c[k] = (t0 + k < p.n_tiles) ? tc[t0 + k] : 0u;
+    const uint32_t refs = c[0] + c[1] + c[2] + c[3];
+    const uint32_t ne = (c[0] != 0u) + (c[1] != 0u) + (c[2] != 0u) + (c[3] != 0u);
+    const uint32_t ex_refs = block_exclusive_scan(refs, &s_total_refs, warp_sums);
+    const uint32_t ex_ne = block_exclusive_scan(ne, &s_total_ne, warp_sums);
     if (threadIdx.x == 0) {
         s_base_refs = atomicAdd(&p.counters->pool_used, s_total_refs);
         s_base_work = atomicAdd(&p.counters->n_work, s_total_ne);
         atomicAdd(&p.counters->tiles_touched, s_total_ne);
-        atomicMax(&p.counters->tri_needed, p.tri_count[f]);
-        if (p.overflow) {
-            atomicMax(&p.overflow->tri_needed, p.tri_count[f]);
-            atomicMax(&p.overflow->pool_needed, s_base_refs + s_total_refs);
+        if (p.overflow) atomicMax(&p.overflow->pool_needed, s_base_refs + s_total_refs);
+        if (blockIdx.x == 0) {
+            atomicMax(&p.counters->tri_needed, p.tri_count[f]);
+            if (p.overflow) atomicMax(&p.overflow->tri_needed, p.tri_count[f]);
         }
     }
     __syncthreads();
     uint32_t off = s_base_refs + ex_refs;
     uint32_t wi = s_base_work + ex_ne;
     uint32_t* to = p.tile_offset + (size_t)f * p.n_tiles;
-    for (int t = t0; t < t1; t++) {
-        uint32_t c = tc[t];
-        to[t] = off;
-        if (c) {
-            uint32_t tx = (uint32_t)(t % p.tiles_x), ty = (uint32_t)(t / p.tiles_x);
-            p.work[wi++] = make_uint4(((uint32_t)f << TILE_BITS) | (ty << 10) | tx, c, off, 0u);
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const int t = t0 + k;
+        if (t < p.n_tiles) {
+            to[t] = off;
+            if (c[k]) {
+                const uint32_t tx = (uint32_t)(t % p.tiles_x), ty = (uint32_t)(t / p.tiles_x);
+                p.work[wi++] = make_uint4(((uint32_t)f << TILE_BITS) | (ty << 10) | tx, c[k], off, 0u);
+            }
+            off += c[k];
         }
-        off += c;
     }
 }
 
