@@ -34,6 +34,9 @@ W, H = 1920, 1080
 FRAMES_PER_STEP = 128
 ORBIT = 1024
 SCENE = "african_head"
+# dram__bytes_read.sum + dram__bytes_write.sum of one raster_main launch (128 frames) in the committed ncu --set full
+# capture of this very command (profiles/r01_v3_step_kernels.md): 184.77 MB + 2.15 GB; per frame, scaled to the launch
+NCU_RASTER_MAIN_DRAM_BYTES_PER_FRAME = (184.77e6 + 2.15e9) / 128
 T_BLINN = 7  # texel bytes per main-pass fragment: 3 (diffuse BGR) + 4 (shadow-map RGBA8 texel), SURVEY.md §8(d)
 METRIC = "frames/s at 1080p, shadowed Blinn (ShadowShader pass + BlinnShader pass), african_head orbit sweep"
 
@@ -366,7 +369,9 @@ def main():
             "gpu_launches": int(launches),
             "clocks": clk,
             "roofline": {"bound": "hbm", "kernel": "raster_kernel<BLINN, CLEAR_FOLD>", "achieved": achieved, "peak": peak,
-                         "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": NCU_RASTER_MAIN_DRAM_BYTES_PER_FRAME * F,
+                         "traffic_source": "ncu --set full capture under profiles/ (dram bytes read + written per launch)",
+                         "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": bytes_raster_main * F, "ms_per_launch": per_launch_ms},
             "frame_roofline": {"algorithmic_bytes_per_frame": bytes_frame, "achieved": bytes_frame * F / (gpu_ms_step * 1e-3) / 1e9,
                                "frac": bytes_frame * F / (gpu_ms_step * 1e-3) / 1e9 / peak, "unit": "GB/s",
