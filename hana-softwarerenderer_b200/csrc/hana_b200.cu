@@ -709,7 +709,9 @@ static int run_pass(hana_ctx* ctx, const PassDesc& d) {
         HANA_TRY(grow(&sc.tri_rec, &sc.tri_total, tri_total * 4, ctx));
         HANA_TRY(grow(&sc.tri_attr, &sc.attr_total, tri_total * MAX_ATTR_QUADS, ctx));
         HANA_TRY(grow(&sc.tri_count, &sc.frames_cap, (size_t)d.n_frames, ctx));
-        HANA_TRY(grow(&sc.tile_arrays, &sc.tile_arr_cap, tiles_total * 3, ctx));
+        const int tile_rows = (int)((n_tiles + 31) / 32);
+        const size_t tiles_pad_total = (size_t)tile_rows * 32 * d.n_frames;
+        HANA_TRY(grow(&sc.tile_arrays, &sc.tile_arr_cap, tiles_pad_total * 2 + tiles_total, ctx));
         HANA_TRY(grow(&sc.work, &sc.work_cap, tiles_total, ctx));
         if (!sc.tile_recs) HANA_TRY(grow(&sc.tile_recs, &sc.pool_cap, std::max<size_t>(tri_total * 2, 65536) * 4, ctx));
 
@@ -728,8 +730,10 @@ static int run_pass(hana_ctx* ctx, const PassDesc& d) {
         p.tri_cap = tri_cap;
         p.tri_count = sc.tri_count;
         p.tile_count = sc.tile_arrays;
-        p.tile_cursor = sc.tile_arrays + tiles_total;
-        p.tile_offset = sc.tile_arrays + 2 * tiles_total;
+        p.tile_cursor = sc.tile_arrays + tiles_pad_total;
+        p.tile_offset = sc.tile_arrays + 2 * tiles_pad_total;
+        p.tile_rows = tile_rows;
+        p.tile_pad = tile_rows * 32;
         p.tile_recs = sc.tile_recs;
         p.pool_cap = (uint32_t)std::min<size_t>(sc.pool_cap / 4, 0xFFFFFFFFull);
         p.work = sc.work;
@@ -740,7 +744,7 @@ static int run_pass(hana_ctx* ctx, const PassDesc& d) {
         /* zero: counters, per-frame triangle counts, tile counts + cursors (contiguous) */
         CU_TRY(cudaMemsetAsync(sc.counters, 0, sizeof(PassCounters), st));
         CU_TRY(cudaMemsetAsync(sc.tri_count, 0, sizeof(uint32_t) * d.n_frames, st));
-        CU_TRY(cudaMemsetAsync(sc.tile_arrays, 0, sizeof(uint32_t) * 2 * tiles_total, st));
+        CU_TRY(cudaMemsetAsync(sc.tile_arrays, 0, sizeof(uint32_t) * 2 * tiles_pad_total, st));
 
         cudaEvent_t ea, eb;
         if (nfaces > 0) {

@@ -76,9 +76,10 @@ struct PassParams {
     float4* tri_attr;     /* [n_frames][tri_cap][attr_quads] */
     uint32_t tri_cap;
     uint32_t* tri_count;  /* [n_frames] */
-    uint32_t* tile_count; /* [n_frames][n_tiles] */
-    uint32_t* tile_offset;
-    uint32_t* tile_cursor;
+    uint32_t* tile_count; /* [n_frames][tile_pad], indexed through tile_slot(): see there */
+    uint32_t* tile_offset; /* [n_frames][n_tiles] */
+    uint32_t* tile_cursor; /* [n_frames][tile_pad], tile_slot() */
+    int tile_pad, tile_rows; /* tile_pad = 32 * tile_rows >= n_tiles */
     float4* tile_recs;    /* pool of raster records (4 x float4 each), grouped per (frame, tile) */
     uint32_t pool_cap;    /* in records */
     uint4* work;          /* [n_frames*n_tiles] non-empty tiles: {item, count, offset, 0} */
@@ -86,6 +87,10 @@ struct PassParams {
     OverflowRecord* overflow; /* optional */
     float* dbg_v2f;       /* optional: [tri_cap][39] post-clip v2f of frame 0 (stage tests) */
 };
+
+/* Where tile t of a frame keeps its counter / list cursor. The L2 serialises atomics that fall into the same line, and
+ * the triangles of a warp touch neighbouring tiles, so neighbours are kept 32 "rows" apart instead of 4 bytes apart. */
+__device__ __forceinline__ int tile_slot(const PassParams& p, int t) { return (t & 31) * p.tile_rows + (t >> 5); }
 
 struct RasterParams {
     PassParams p;
@@ -216,9 +221,9 @@ __device__ __forceinline__ void store_triangle(const PassParams& p, int f, uint3
 __device__ __forceinline__ void count_tiles(const PassParams& p, int f, const TriRecord& r) {
     int tx0 = (int)(r.bbx & 0xFFFFu) >> 4, tx1 = (int)(r.bbx >> 16) >> 4;
     int ty0 = (int)(r.bby & 0xFFFFu) >> 4, ty1 = (int)(r.bby >> 16) >> 4;
-    uint32_t* tc = p.tile_count + (size_t)f * p.n_tiles;
+    uint32_t* tc = p.tile_count + (size_t)f * p.tile_pad;
     for (int ty = ty0; ty <= ty1; ty++)
-        for (int tx = tx0; tx <= tx1; tx++) atomicAdd(tc + ty * p.tiles_x + tx, 1u);
+        for (int tx = tx0; tx <= tx1; tx++) atomicAdd(tc + tile_slot(p, ty * p.tiles_x + tx), 1u);
 }
 
 /* Rare path: the face is not trivially accepted. Sutherland-Hodgman in local
@@ -335,10 +340,10 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_kernel(PassParams p) {
     __shared__ uint32_t s_total_refs, s_total_ne, s_base_refs, s_base_work;
     const int f = blockIdx.y;
     const int t0 = blockIdx.x * SCAN_CHUNK + (int)threadIdx.x * 4;
-    const uint32_t* tc = p.tile_count + (size_t)f * p.n_tiles;
+    const uint32_t* tc = p.tile_count + (size_t)f * p.tile_pad;
     uint32_t c[4];
 #pragma unroll
-    for (int k = 0; k < 4; k++) c[k] = (t0 + k < p.n_tiles) ? tc[t0 + k] : 0u;
+    for (int k = 0; k < 4; k++) c[k] = (t0 + k < p.n_tiles) ? tc[tile_slot(p, t0 + k)] : 0u;
     const uint32_t refs = c[0] + c[1] + c[2] + c[3];
     const uint32_t ne = (c[0] != 0u) + (c[1] != 0u) + (c[2] != 0u) + (c[3] != 0u);
     const uint32_t ex_refs = block_exclusive_scan(refs, &s_total_refs, warp_sums);
@@ -402,7 +407,7 @@ __global__ void __launch_bounds__(256) fill_kernel(PassParams p) {
     }
     const int excl = incl - nt;
     const int total = __shfl_sync(FULL, incl, 31);
-    uint32_t* cur = p.tile_cursor + (size_t)f * p.n_tiles;
+    uint32_t* cur = p.tile_cursor + (size_t)f * p.tile_pad;
     const uint32_t* to = p.tile_offset + (size_t)f * p.n_tiles;
     for (int base = 0; base < total; base += 32) {
         const int k = base + (int)lane;
@@ -420,7 +425,7 @@ __global__ void __launch_bounds__(256) fill_kernel(PassParams p) {
             const float4 q0 = __ldg(rec), q1 = __ldg(rec + 1), q2 = __ldg(rec + 2), q3 = __ldg(rec + 3);
             const int row = local / jntx;
             const int t = (jty0 + row) * p.tiles_x + jtx0 + (local - row * jntx);
-            const uint32_t s = atomicAdd(cur + t, 1u);
+            const uint32_t s = atomicAdd(cur + tile_slot(p, t), 1u);
             float4* d = p.tile_recs + ((size_t)__ldg(to + t) + s) * 4;
             d[0] = q0;
             d[1] = q1;
@@ -474,8 +479,8 @@ __device__ __forceinline__ void clear_slots(const RasterParams& q, RasterSmem<MO
                                             uint32_t n_slots) {
     const PassParams& p = q.p;
     const uint32_t s = base + (threadIdx.x & 31u);
-    if (s < n_slots && p.tile_count[s] == 0u) {
-        const int f = (int)(s / (uint32_t)p.n_tiles), t = (int)(s % (uint32_t)p.n_tiles);
+    const int f = (int)(s / (uint32_t)p.n_tiles), t = (int)(s % (uint32_t)p.n_tiles);
+    if (s < n_slots && p.tile_count[(size_t)f * p.tile_pad + tile_slot(p, t)] == 0u) {
         const int tx = t % p.tiles_x, ty = t / p.tiles_x;
         if (q.use_tma) {
             if (MODE == MODE_SHADOW_R8) {
