@@ -229,3 +229,42 @@ def test_dropin_graphics_draw_triangle(hana, horacle):
         assert np.abs(c0.astype(int) - c1.astype(int)).max() <= 1 and np.array_equal(c0[..., 3], c1[..., 3])
         for r in (ref, gpu, ref2, gpu2):
             r.close()
+
+
+@pytest.mark.parametrize("copies", [2, 40])
+def test_equal_depths_later_submission_wins(hana, horacle, port, ctx, blob, copies):
+    """The same faces submitted several times with different uvs: every fragment of a later copy ties in depth with the
+    earlier one and the reference lets it pass (z > stored is false, graphics.cpp:359), so the LAST copy owns every pixel.
+    40 copies put more than 32 records into most tiles, so winners and ties cross the 32-record staging chunks; the
+    shadow pass resolves the same ties in its own (in-loop) way."""
+    W, Hh = 256, 192
+    parts = []
+    for k in range(copies):
+        a = blob.a2v.copy()
+        a[:, 6:8] = (a[:, 6:8] * (0.5 + 0.5 * k / copies)) % 1.0
+        parts.append(a)
+    order = np.arange(copies)
+    order[1:] = np.random.default_rng(3).permutation(order[1:])        # submission order != any spatial order
+    a2v = np.concatenate([parts[k] for k in order])
+    sc = hana.Scene("dup", a2v, blob.diffuse, blob.normal)
+    u = hana.default_uniforms(W, Hh, True)
+    hu = horacle.HanaUniforms.from_bytes(u.to_bytes())
+    col, dep, pid, scol, sdep = oracle_two_pass(port, horacle, horacle.BLINN, hu, sc, W, Hh)
+    nf = blob.a2v.shape[0] // 3
+    assert (pid[pid != 0xFFFFFFFF] // 8 >= (copies - 1) * nf).all()     # the oracle agrees: last copy everywhere
+    model, dtex, ntex = sc.upload(ctx)
+    frame, shadow = ctx.renderbuffer(W, Hh), ctx.renderbuffer(W, Hh)
+    for rb in (frame, shadow):
+        rb.clear_color(0, 0, 0, 1)
+        rb.clear_depth(FLT_MAX)
+    ctx.draw(shadow, model, hana.SHADOW, u)
+    gpid = ctx.draw(frame, model, hana.BLINN, u, dtex, ntex, shadow, want_primid=True)
+    gcol, gdep = frame.download()
+    check(compare_frames(gcol, gdep, col, dep, gpid, pid), W * Hh)
+    sw = ctx.sweep(W, Hh, 1)                                            # sweep: SHADOW_R8 in-loop resolve + CLEAR_FOLD
+    sw.render(model, hana.BLINN, [u], dtex, ntex)
+    scol2, sdep2 = sw.download(0)
+    assert np.array_equal(sdep2.view(np.uint32), dep.view(np.uint32))
+    assert np.abs(scol2[..., :3].astype(int) - col[..., :3].astype(int)).max() <= 1
+    for o in (sw, frame, shadow, model, dtex, ntex):
+        o.close()
