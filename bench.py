@@ -373,9 +373,9 @@ def main():
                          "traffic_source": "ncu --set full capture under profiles/ (dram bytes read + written per launch)",
                          "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": bytes_raster_main * F, "ms_per_launch": per_launch_ms},
-            "frame_roofline": {"algorithmic_bytes_per_frame": bytes_frame, "achieved": bytes_frame * F / (gpu_ms_step * 1e-3) / 1e9,
-                               "frac": bytes_frame * F / (gpu_ms_step * 1e-3) / 1e9 / peak, "unit": "GB/s",
-                               "note": "SURVEY.md §8(d) bytes of the whole frame over the summed kernel time of a step"},
+            "frame_roofline": {"algorithmic_bytes_per_frame": bytes_frame, "achieved": bytes_frame * value / world / 1e9,
+                               "frac": bytes_frame * value / world / 1e9 / peak, "unit": "GB/s",
+                               "note": "SURVEY.md §8(d) bytes of the whole frame (both passes) over the step time per GPU"},
             "kernel_ms_per_step": {k: v / args.steps for k, v in kernel_ms.items()},
             "cpu_baseline": cpu,
         }

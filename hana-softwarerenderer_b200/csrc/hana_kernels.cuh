@@ -627,6 +627,7 @@ __global__ void __launch_bounds__(RW_THREADS, ShaderAttrs<SHADER>::LIT ? 6 : 7)
         if (cur.x == WORK_INVALID) break;
         cur.y = __shfl_sync(FULL, e_cur.y, 0);
         cur.z = __shfl_sync(FULL, e_cur.z, 0);
+        __syncwarp(); /* every lane is done with the previous tile's shared memory (fu, ord, tri) */
         uint4 e_nxt = make_uint4(WORK_INVALID, 0u, 0u, 0u);
         uint32_t i_nn = 0, clr_base = 0;
         if (lane == 0) {
