@@ -27,6 +27,7 @@
 #include <cuda_runtime.h>
 
 #include "hana_core.cuh"
+#include "hana_pack.cuh"
 
 namespace hana {
 
@@ -436,29 +437,56 @@ __global__ void __launch_bounds__(256) fill_kernel(PassParams p) {
 }
 
 /* ---- raster ------------------------------------------------------------------
- * One WARP per 16x16 tile, no CTA-wide barrier anywhere in the tile loop (v2 spent a third of its
- * time at __syncthreads waiting for the slowest of 8 warps). A lane owns 8 pixels of the tile: pixel
- * (lane & 7, lane >> 3) of each of the eight 8x4 sub-blocks (2 across, 4 down). The tile's records
- * are staged 32 at a time in the warp's private shared memory; lane j also computes which sub-blocks
- * record j's pixel range meets, so the triangle loop is warp-uniform and skips sub-blocks without a
- * single per-pixel instruction. The (min depth, max key) resolve lives in registers as
- * {depth, list ordinal} per pixel; after the last record the state is parked in shared memory and
- * the winners are shaded one sub-block at a time (weights recomputed from the winning record, which
- * costs less than carrying three weights per pixel through the resolve loop). The warp's tile is
- * flushed with TMA stores issued by lane 0; warps never wait for each other. */
+ * One WARP per 16x16 tile, no CTA-wide barrier anywhere in the tile loop. A lane owns 8 pixels of the
+ * tile: pixel (lane & 7, lane >> 3) of each of the eight 8x4 sub-blocks (2 across, 4 down; sub-block
+ * sb = row quarter * 2 + column half). The tile's records are staged 32 at a time in the warp's
+ * private shared memory by lane j for record j, which also computes which sub-blocks the record's pixel
+ * range meets, so the triangle loop is warp-uniform and skips rows of sub-blocks without a per-pixel
+ * instruction.
+ *
+ * Arithmetic is packed two pixels at a time (hana_pack.cuh): the two pixels of a lane that share a row
+ * (column halves 0 and 1) go through every multiply / add of graphics.cpp:222-233 and :186-194 as the two
+ * halves of one FFMA2, with the record's scalars as broadcast operands. Per record: 3 packed operations
+ * for the x-dependent terms, 3 per pair of rows for the y-dependent ones, then 5 per row of 64 pixels and
+ * one 3-input max + one compare per pixel for the inside test; covered pixels take 14 more packed
+ * operations for the exact weights and the depth. The (min depth, max key) resolve lives in registers as
+ * {depth, triangle slot} per pixel; the three weights of a fragment that wins are parked in shared memory
+ * (they cost three stores where the fragment wins, which happens ~1.01 times per visible pixel), so the
+ * shading stage neither re-fetches a record nor recomputes a weight. The warp's tile is flushed with TMA
+ * stores issued by lane 0; warps never wait for each other.
+ *
+ * Every kept triangle has u.z < 0 (u.z = -2 x the screen area of a counter-clockwise triangle, and
+ * graphics.cpp:320 culled the others), except slivers whose two area computations round to different
+ * signs. Those are staged with B and C exchanged in the coverage constants, which negates u.x<->u.y, their
+ * sum, u.z and the threshold difference exactly, so one code path (the u.z < 0 one) serves every record;
+ * their two quotients swap places again when the weights are formed. */
 constexpr int RW_WARPS = 4;
+#ifndef HANA_OCC_LIT
+#define HANA_OCC_LIT 6 /* resident CTAs per SM the lit shaders' rasteriser is compiled for (register cap 80) */
+#endif
+#ifndef HANA_OCC_OTHER
+#define HANA_OCC_OTHER 7
+#endif
 constexpr int RW_THREADS = RW_WARPS * 32;
 constexpr int RW_CHUNK = 32;
+constexpr int RW_REC_Q = 5; /* float4 per staged record */
 constexpr uint32_t ORD_NONE = 0xFFFFFFFFu;
 
+/* Staged record (shared memory), 5 x float4:
+ *   q0 = ax, ay, s0x, s0y         q1 = s1x, s1y, uz (< 0), thr
+ *   q2 = bbox centre x, centre y, half extent x, half extent y   (exact: sums of two 16-bit integers, halved)
+ *   q3 = d0, d1, d2, 1/uz         q4 = triangle slot, order key, B/C exchanged flag, sub-block mask */
 template <int MODE>
 struct alignas(128) WarpTile {
     /* TMA sources/destinations first: each 128-byte aligned */
-    uint32_t color[MODE == MODE_SHADOW_R8 ? 32 : TILE_PIX]; /* box 16x16 u32 */
+    uint32_t color[MODE == MODE_SHADOW_R8 ? 32 : TILE_PIX]; /* box 16x16 u32; CLEAR_FOLD: holds the parked w0 of a pixel until it is shaded */
     float depth[MODE == MODE_SHADOW_R8 ? 32 : TILE_PIX];
     uint8_t r8[MODE == MODE_SHADOW_R8 ? TILE_PIX : 128];    /* box 16x16 u8 */
-    uint32_t ord[MODE == MODE_SHADOW_R8 ? 32 : TILE_PIX];   /* winning list ordinal per pixel, parked for shading */
-    float4 tri[RW_CHUNK * 4];                               /* staged raster records */
+    uint32_t ord[MODE == MODE_SHADOW_R8 ? 32 : TILE_PIX];   /* winning triangle slot per pixel, parked for shading */
+    float pw1[MODE == MODE_SHADOW_R8 ? 32 : TILE_PIX];      /* parked weights of the winning fragment */
+    float pw2[MODE == MODE_SHADOW_R8 ? 32 : TILE_PIX];
+    float pw0_own[MODE == MODE_RMW ? TILE_PIX : 32];        /* RMW: color[] holds the target's pixels */
+    float4 tri[RW_CHUNK * RW_REC_Q];                        /* staged raster records */
     float4 sattr[MODE == MODE_SHADOW_R8 ? RW_CHUNK * 2 : 1]; /* SHADOW_R8: their (1/w, clip z) blocks */
     FragUniforms fu;                                        /* the tile's frame: what fragment() reads */
     alignas(8) uint64_t bar;
@@ -517,9 +545,9 @@ __device__ __forceinline__ uint4 fetch_work(const PassParams& p, uint32_t idx, u
 
 /* Sub-blocks (bit r*2+c: column half c, row quarter r) of the tile at (X0,Y0) that the pixel range meets.
  * The range is known to meet the tile (that is why the record is in this tile's list). */
-__device__ __forceinline__ uint32_t subblock_mask(uint32_t bbx, uint32_t bby, int X0, int Y0) {
-    const int cx0 = max((int)(bbx & 0xFFFFu) - X0, 0) >> 3, cx1 = min((int)(bbx >> 16) - X0, TILE - 1) >> 3;
-    const int ry0 = max((int)(bby & 0xFFFFu) - Y0, 0) >> 2, ry1 = min((int)(bby >> 16) - Y0, TILE - 1) >> 2;
+__device__ __forceinline__ uint32_t subblock_mask(int x0, int x1, int y0, int y1, int X0, int Y0) {
+    const int cx0 = max(x0 - X0, 0) >> 3, cx1 = min(x1 - X0, TILE - 1) >> 3;
+    const int ry0 = max(y0 - Y0, 0) >> 2, ry1 = min(y1 - Y0, TILE - 1) >> 2;
     const uint32_t cm = (2u << cx1) - (1u << cx0);        /* 2 bits */
     const uint32_t rm = (2u << ry1) - (1u << ry0);        /* 4 bits */
     const uint32_t spread = (rm & 1u) | ((rm & 2u) << 1) | ((rm & 4u) << 2) | ((rm & 8u) << 3);
@@ -576,7 +604,7 @@ __device__ __forceinline__ void shade_fragment(const FragUniforms& fu, const flo
 }
 
 template <int SHADER, int MODE>
-__global__ void __launch_bounds__(RW_THREADS, ShaderAttrs<SHADER>::LIT ? 6 : 7)
+__global__ void __launch_bounds__(RW_THREADS, ShaderAttrs<SHADER>::LIT ? HANA_OCC_LIT : HANA_OCC_OTHER)
     raster_kernel(RasterParams q, const __grid_constant__ CUtensorMap tm_color, const __grid_constant__ CUtensorMap tm_depth,
                   const __grid_constant__ CUtensorMap tm_r8) {
     constexpr int NQ = ShaderAttrs<SHADER>::NQ;
@@ -584,13 +612,14 @@ __global__ void __launch_bounds__(RW_THREADS, ShaderAttrs<SHADER>::LIT ? 6 : 7)
     /* SHADOW_R8 (always the ShadowShader): its one-attribute fragment() is evaluated right where a fragment wins the
      * resolve and the byte rides in the top 8 bits of the state word, so nothing is parked or re-fetched afterwards */
     constexpr bool INLOOP = (MODE == MODE_SHADOW_R8);
-    constexpr uint32_t ORD_MASK = INLOOP ? 0x00FFFFFFu : 0xFFFFFFFFu;
+    constexpr uint32_t SLOT_MASK = INLOOP ? 0x00FFFFFFu : 0xFFFFFFFFu;
     __shared__ RasterSmem<MODE> sm;
     const PassParams& p = q.p;
     const unsigned lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
     WarpTile<MODE>& wt = sm.w[wid];
     const int lx = (int)(lane & 7u), ly = (int)(lane >> 3);
     const bool tma = q.use_tma != 0;
+    float* const pw0 = MODE == MODE_RMW ? wt.pw0_own : reinterpret_cast<float*>(wt.color);
 
     if (p.counters->pool_used > p.pool_cap) return; /* lists are incomplete: host re-runs with a larger pool */
     const uint32_t n_work = p.counters->n_work;
@@ -642,11 +671,14 @@ __global__ void __launch_bounds__(RW_THREADS, ShaderAttrs<SHADER>::LIT ? 6 : 7)
         const int X0 = tx * TILE, Y0 = ty * TILE;
         const uint32_t cnt = cur.y;
         const float4* list = p.tile_recs + (size_t)cur.z * 4;
+        const float4* frame_rec = p.tri_rec + (size_t)f * p.tri_cap * 4; /* the frame's records by slot: tie-breaks, primitive ids */
         if (ShaderAttrs<SHADER>::READS_UNIFORMS && lane < sizeof(FragUniforms) / 16) /* read again only after the __syncwarp()s of the record loop */
             reinterpret_cast<float4*>(&wt.fu)[lane] = __ldg(reinterpret_cast<const float4*>(&p.uniforms[f].frag) + lane);
         const float fpx0 = (float)(X0 + lx), fpx1 = (float)(X0 + 8 + lx);
         const float fpy0 = (float)(Y0 + ly), fpy1 = (float)(Y0 + 4 + ly), fpy2 = (float)(Y0 + 8 + ly), fpy3 = (float)(Y0 + 12 + ly);
+        const f2 FPX = f2_make(fpx0, fpx1), FPY01 = f2_make(fpy0, fpy1), FPY23 = f2_make(fpy2, fpy3);
         const int ipx0 = X0 + lx, ipy0 = Y0 + ly;
+        const int pix0 = ly * TILE + lx; /* the lane's pixel in sub-block 0; sub-block sb adds (sb >> 1) * 64 + (sb & 1) * 8 */
 
         float bz[8];
         uint32_t bj[8];
@@ -666,7 +698,7 @@ __global__ void __launch_bounds__(RW_THREADS, ShaderAttrs<SHADER>::LIT ? 6 : 7)
                 mbar_wait(&wt.bar, load_phase);
                 load_phase ^= 1u;
 #pragma unroll
-                for (int sb = 0; sb < 8; sb++) bz[sb] = wt.depth[((sb >> 1) * 4 + ly) * TILE + (sb & 1) * 8 + lx];
+                for (int sb = 0; sb < 8; sb++) bz[sb] = wt.depth[pix0 + (sb >> 1) * 64 + (sb & 1) * 8];
             } else {
 #pragma unroll
                 for (int sb = 0; sb < 8; sb++) {
@@ -674,70 +706,140 @@ __global__ void __launch_bounds__(RW_THREADS, ShaderAttrs<SHADER>::LIT ? 6 : 7)
                     if (px < p.W && py < p.H) bz[sb] = q.depth[(size_t)f * q.frame_stride + (size_t)py * p.W + px];
                 }
             }
+        } else if (MODE == MODE_CLEAR_FOLD && tma) {
+            if (lane == 0) tma_wait_read0(); /* the previous tile's stores have drained the staging tile: weights are parked in it below */
+            __syncwarp();
         }
+
+        /* Equal depths (rare): graphics.cpp:359 is "skip if z > stored" in submission order, so a fragment as deep as the
+         * target's value passes (LEQUAL) and of two equally deep fragments the later submission wins. */
+        auto wins_tie = [&](const int sb, const uint32_t key) -> bool {
+            if (bj[sb] == ORD_NONE) return true;
+            const uint32_t kb = __float_as_uint(__ldg(frame_rec + (size_t)(bj[sb] & SLOT_MASK) * 4 + 2).w);
+            return key > kb;
+        };
 
         for (uint32_t c0 = 0; c0 < cnt; c0 += RW_CHUNK) {
             const int n = (int)min((uint32_t)RW_CHUNK, cnt - c0);
             __syncwarp(); /* previous chunk fully consumed */
-#pragma unroll
-            for (int k = 0; k < 4; k++) {
-                const int idx = k * 32 + (int)lane;
-                if (idx < n * 4) wt.tri[idx] = __ldg(list + (size_t)c0 * 4 + idx);
-            }
-            uint32_t mask = 0;
-            if ((int)lane < n) {
-                const float4 b = __ldg(list + ((size_t)c0 + lane) * 4 + 2);
-                mask = subblock_mask(__float_as_uint(b.x), __float_as_uint(b.y), X0, Y0);
+            if ((int)lane < n) { /* lane j stages record j */
+                const float4* rec = list + ((size_t)c0 + lane) * 4;
+                float4 a0 = __ldg(rec), a1 = __ldg(rec + 1);
+                const float4 a2 = __ldg(rec + 2), a3 = __ldg(rec + 3);
+                const uint32_t bbx = __float_as_uint(a2.x), bby = __float_as_uint(a2.y);
+                const int x0 = (int)(bbx & 0xFFFFu), x1 = (int)(bbx >> 16), y0 = (int)(bby & 0xFFFFu), y1 = (int)(bby >> 16);
+                const uint32_t mask = subblock_mask(x0, x1, y0, y1, X0, Y0);
+                float swapped = 0.f;
+                if (a1.z > 0.f) { /* sliver whose u.z rounded positive: exchange B and C in the coverage constants */
+                    a0 = make_float4(a0.x, a0.y, a0.w, a0.z);
+                    a1 = make_float4(a1.y, a1.x, -a1.z, a1.w);
+                    swapped = 1.f;
+                }
+                float4* dst = wt.tri + lane * RW_REC_Q;
+                dst[0] = a0;
+                dst[1] = a1;
+                dst[2] = make_float4((float)(x0 + x1) * 0.5f, (float)(y0 + y1) * 0.5f, (float)(x1 - x0) * 0.5f, (float)(y1 - y0) * 0.5f);
+                dst[3] = swapped != 0.f ? make_float4(a3.x, a3.y, a3.z, -a3.w) : a3;
+                dst[4] = make_float4(a2.z, a2.w, swapped, __uint_as_float(mask));
                 if (INLOOP) {
-                    const float4* ap = p.tri_attr + ((size_t)f * p.tri_cap + __float_as_uint(b.z)) * 2;
+                    const float4* ap = p.tri_attr + ((size_t)f * p.tri_cap + __float_as_uint(a2.z)) * 2;
                     wt.sattr[lane * 2] = __ldg(ap);
                     wt.sattr[lane * 2 + 1] = __ldg(ap + 1);
                 }
             }
             __syncwarp();
             for (int j = 0; j < n; j++) {
-                const uint32_t m = __shfl_sync(FULL, mask, j);
-                const float4 r0 = wt.tri[j * 4 + 0]; /* ax, ay, s0x, s0y */
-                const float4 r1 = wt.tri[j * 4 + 1]; /* s1x, s1y, uz, thr */
-                const float4 r2 = wt.tri[j * 4 + 2]; /* bbx, bby, attr index, key */
-                const uint32_t bbx = __float_as_uint(r2.x), bby = __float_as_uint(r2.y);
-                const int x0 = (int)(bbx & 0xFFFFu), dx = (int)(bbx >> 16) - x0;
-                const int y0 = (int)(bby & 0xFFFFu), dy = (int)(bby >> 16) - y0;
+                const float4 r0 = wt.tri[j * RW_REC_Q + 0]; /* ax, ay, s0x, s0y */
+                const float4 r1 = wt.tri[j * RW_REC_Q + 1]; /* s1x, s1y, uz, thr */
+                const float4 r4 = wt.tri[j * RW_REC_Q + 4]; /* slot, key, exchanged, mask */
+                const uint32_t m = __float_as_uint(r4.w);
+                /* x-dependent terms of cross(s0, s1) for both column halves: graphics.cpp:224-229 */
+                const f2 S0Z = f2_sub(f2_dup(r0.x), FPX);          /* A.x - P.x */
+                const f2 T2 = f2_mul(S0Z, f2_dup(r1.y));           /* s0.z * s1.y */
+                const f2 T3 = f2_mul(S0Z, f2_dup(r1.x));           /* s0.z * s1.x */
 #pragma unroll
-                for (int sb = 0; sb < 8; sb++) {
-                    if (m & (1u << sb)) { /* warp-uniform */
-                        const float fpx = (sb & 1) ? fpx1 : fpx0;
-                        const float fpy = (sb >> 1) == 0 ? fpy0 : ((sb >> 1) == 1 ? fpy1 : ((sb >> 1) == 2 ? fpy2 : fpy3));
-                        float ux, uy, su;
-                        bool cov = coverage_test(r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w, fpx, fpy, ux, uy, su);
-                        if (cov) {
-                            /* the reference only visits pixels of its clamped bounding box: graphics.cpp:339-351 */
-                            const int px = ipx0 + (sb & 1) * 8, py = ipy0 + (sb >> 1) * 4;
-                            if ((unsigned)(px - x0) <= (unsigned)dx && (unsigned)(py - y0) <= (unsigned)dy) {
-                                const float4 r3 = wt.tri[j * 4 + 3]; /* d0, d1, d2, 1/uz */
-                                float w0, w1, w2;
-                                barycentric_weights(ux, uy, su, r1.z, r3.w, w0, w1, w2);
-                                const float z = interpolate_depth(r3.x, r3.y, r3.z, w0, w1, w2);
-                                bool win;
-                                if (bj[sb] == ORD_NONE) {
-                                    win = !(z > bz[sb]); /* graphics.cpp:359 against the target's depth */
-                                } else {
-                                    win = z < bz[sb];
-                                    if (z == bz[sb]) { /* rare: equal depths, the later submission wins */
-                                        const uint32_t kb = __float_as_uint(__ldg(list + (size_t)(bj[sb] & ORD_MASK) * 4 + 2).w);
-                                        win = __float_as_uint(r2.w) > kb;
-                                    }
-                                }
-                                if (win) {
-                                    bz[sb] = z;
-                                    bj[sb] = c0 + (uint32_t)j;
-                                    if (INLOOP) { /* ShadowShader::fragment IShader.cpp:176-180 on the winning fragment */
-                                        const float4 rw = wt.sattr[j * 2], a = wt.sattr[j * 2 + 1];
-                                        const VaryingWeights vw = varying_weights(w0, w1, w2, rw.x, rw.y, rw.z);
-                                        const float attr0 = interp(vw, a.x, a.y, a.z);
-                                        float rgb[3];
-                                        fragment_shader<HANA_SHADER_SHADOW>(wt.fu, &attr0, q.diffuse, q.normal, q.shadow, rgb);
-                                        bj[sb] |= (colour_bytes(rgb) & 255u) << 24;
+                for (int rp = 0; rp < 2; rp++) {
+                    if (m & (0xFu << (4 * rp))) { /* warp-uniform */
+                        /* y-dependent terms for two row quarters */
+                        const f2 S1Z = f2_sub(f2_dup(r0.y), rp ? FPY23 : FPY01); /* A.y - P.y */
+                        const f2 T1 = f2_mul(f2_dup(r0.w), S1Z);                  /* s0.y * s1.z */
+                        const f2 T4 = f2_mul(f2_dup(r0.z), S1Z);                  /* s0.x * s1.z */
+#pragma unroll
+                        for (int h = 0; h < 2; h++) {
+                            const int r = rp * 2 + h;
+                            if (m & (3u << (2 * r))) { /* warp-uniform */
+                                const f2 UX = f2_sub(f2_dup(f2_half(T1, h)), T2);
+                                const f2 UY = f2_sub(T3, f2_dup(f2_half(T4, h)));
+                                const f2 S = f2_add(UX, UY);
+                                const f2 D = f2_sub(S, f2_dup(r1.z));
+                                const f2 E = f2_sub(f2_dup(-r1.w), D);
+                                /* coverage_test() for u.z < 0: u.x <= 0, u.y <= 0, d >= -thr */
+                                const bool cA = fmax3(f2_lo(UX), f2_lo(UY), f2_lo(E)) <= 0.f;
+                                const bool cB = fmax3(f2_hi(UX), f2_hi(UY), f2_hi(E)) <= 0.f;
+                                if (cA || cB) {
+                                    /* the reference only visits pixels of its clamped bounding box: graphics.cpp:339-351 */
+                                    const float4 r2 = wt.tri[j * RW_REC_Q + 2];
+                                    const float fpy = f2_half(rp ? FPY23 : FPY01, h);
+                                    const bool rowin = fabsf(fpy - r2.y) <= r2.w;
+                                    const bool inA = cA && rowin && fabsf(f2_lo(FPX) - r2.x) <= r2.z;
+                                    const bool inB = cB && rowin && fabsf(f2_hi(FPX) - r2.x) <= r2.z;
+                                    if (inA || inB) {
+                                        const float4 r3 = wt.tri[j * RW_REC_Q + 3]; /* d0, d1, d2, 1/uz */
+                                        const f2 RUZ = f2_dup(r3.w), NUZ = f2_dup(-r1.z);
+                                        /* (1 - (u.x+u.y)/u.z, u.y/u.z, u.x/u.z): graphics.cpp:231 */
+                                        const f2 W0 = f2_fma(f2_div_by_recip(S, NUZ, RUZ), f2_negone(), f2_one());
+                                        f2 W1 = f2_div_by_recip(UY, NUZ, RUZ);
+                                        f2 W2 = f2_div_by_recip(UX, NUZ, RUZ);
+                                        if (r4.z != 0.f) { /* B and C were exchanged: so were u.x and u.y */
+                                            const f2 t = W1;
+                                            W1 = W2;
+                                            W2 = t;
+                                        }
+                                        /* interpolate_depth graphics.cpp:186-194 */
+                                        f2 Z = f2_mul_from_zero(f2_dup(r3.z), W2);
+                                        Z = f2_add(Z, f2_mul(f2_dup(r3.y), W1));
+                                        Z = f2_add(Z, f2_mul(f2_dup(r3.x), W0));
+                                        const uint32_t slot = __float_as_uint(r4.x);
+                                        const float zA = f2_lo(Z), zB = f2_hi(Z);
+                                        bool winA = inA && zA < bz[2 * r], winB = inB && zB < bz[2 * r + 1];
+                                        const bool tieA = inA && zA == bz[2 * r], tieB = inB && zB == bz[2 * r + 1];
+                                        if (tieA || tieB) { /* rare */
+                                            const uint32_t key = __float_as_uint(r4.y);
+                                            if (tieA) winA = wins_tie(2 * r, key);
+                                            if (tieB) winB = wins_tie(2 * r + 1, key);
+                                        }
+                                        if (winA) {
+                                            bz[2 * r] = zA;
+                                            bj[2 * r] = slot;
+                                        }
+                                        if (winB) {
+                                            bz[2 * r + 1] = zB;
+                                            bj[2 * r + 1] = slot;
+                                        }
+                                        if (INLOOP) {
+                                            if (winA || winB) { /* ShadowShader::fragment IShader.cpp:176-180 on the winning fragments */
+                                                const float4 rw = wt.sattr[j * 2], a = wt.sattr[j * 2 + 1];
+                                                /* interpolate_varyings graphics.cpp:205-220 for clip_pos.z */
+                                                const f2 V0 = f2_mul(f2_dup(rw.x), W0), V1 = f2_mul(f2_dup(rw.y), W1), V2 = f2_mul(f2_dup(rw.z), W2);
+                                                const f2 SUM = f2_add(f2_add(V0, V1), V2);
+                                                const f2 NORM = f2_rcp(SUM);
+                                                const f2 AT = f2_mul(f2_add(f2_add(f2_mul(f2_dup(a.x), V0), f2_mul(f2_dup(a.y), V1)), f2_mul(f2_dup(a.z), V2)), NORM);
+                                                if (winA) bj[2 * r] |= shadow_byte(f2_lo(AT)) << 24;
+                                                if (winB) bj[2 * r + 1] |= shadow_byte(f2_hi(AT)) << 24;
+                                            }
+                                        } else {
+                                            const int pix = pix0 + r * 64;
+                                            if (winA) {
+                                                pw0[pix] = f2_lo(W0);
+                                                wt.pw1[pix] = f2_lo(W1);
+                                                wt.pw2[pix] = f2_lo(W2);
+                                            }
+                                            if (winB) {
+                                                pw0[pix + 8] = f2_hi(W0);
+                                                wt.pw1[pix + 8] = f2_hi(W1);
+                                                wt.pw2[pix + 8] = f2_hi(W2);
+                                            }
+                                        }
                                     }
                                 }
                             }
@@ -747,15 +849,15 @@ __global__ void __launch_bounds__(RW_THREADS, ShaderAttrs<SHADER>::LIT ? 6 : 7)
             }
         }
 
-        if (tma && MODE != MODE_RMW) {
-            if (lane == 0) tma_wait_read0(); /* the previous tile's stores have drained the staging tile */
+        if (tma && MODE == MODE_SHADOW_R8) {
+            if (lane == 0) tma_wait_read0(); /* the previous tile's store has drained the staging tile */
             __syncwarp();
         }
         uint32_t covered_acc = 0;
         if (INLOOP) {
 #pragma unroll
             for (int sb = 0; sb < 8; sb++) {
-                const int pix = ((sb >> 1) * 4 + ly) * TILE + (sb & 1) * 8 + lx;
+                const int pix = pix0 + (sb >> 1) * 64 + (sb & 1) * 8;
                 const uint8_t v = (uint8_t)(bj[sb] == ORD_NONE ? 0u : (bj[sb] >> 24));
                 if (q.pixels_covered) covered_acc += __popc(__ballot_sync(FULL, bj[sb] != ORD_NONE));
                 if (tma) {
@@ -770,7 +872,7 @@ __global__ void __launch_bounds__(RW_THREADS, ShaderAttrs<SHADER>::LIT ? 6 : 7)
         /* -- park the resolve state, shade the winners one sub-block at a time (graphics.cpp:362-373) -- */
 #pragma unroll
         for (int sb = 0; sb < 8; sb++) {
-            const int pix = ((sb >> 1) * 4 + ly) * TILE + (sb & 1) * 8 + lx;
+            const int pix = pix0 + (sb >> 1) * 64 + (sb & 1) * 8;
             wt.ord[pix] = bj[sb];
             wt.depth[pix] = bz[sb];
         }
@@ -778,32 +880,28 @@ __global__ void __launch_bounds__(RW_THREADS, ShaderAttrs<SHADER>::LIT ? 6 : 7)
         if (sh.base) sh.base += (size_t)f * q.shadow_frame_stride;
 #pragma unroll 1
         for (int sb = 0; sb < 8; sb++) {
-            const int pix = ((sb >> 1) * 4 + ly) * TILE + (sb & 1) * 8 + lx;
+            const int pix = pix0 + (sb >> 1) * 64 + (sb & 1) * 8;
             const int px = ipx0 + (sb & 1) * 8, py = ipy0 + (sb >> 1) * 4;
             const bool in_frame = px < p.W && py < p.H;
-            const uint32_t j = wt.ord[pix];
+            const uint32_t slot = wt.ord[pix];
             uint32_t col = q.clear_color;
             if (MODE == MODE_RMW) {
                 if (tma) col = wt.color[pix];
-                else if (in_frame && j != ORD_NONE) col = q.color[(size_t)f * q.frame_stride + (size_t)py * p.W + px];
+                else if (in_frame && slot != ORD_NONE) col = q.color[(size_t)f * q.frame_stride + (size_t)py * p.W + px];
             }
-            if (j != ORD_NONE) {
-                const float4* rec = list + (size_t)j * 4;
-                const float4 r0 = __ldg(rec), r1 = __ldg(rec + 1), r2 = __ldg(rec + 2), r3 = __ldg(rec + 3);
-                float ux, uy, su, w0, w1, w2;
-                coverage_test(r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w, (float)px, (float)py, ux, uy, su);
-                barycentric_weights(ux, uy, su, r1.z, r3.w, w0, w1, w2);
-                const float4* ap = p.tri_attr + ((size_t)f * p.tri_cap + __float_as_uint(r2.z)) * NQ;
+            if (slot != ORD_NONE) {
+                const float w0 = pw0[pix], w1 = wt.pw1[pix], w2 = wt.pw2[pix];
+                const float4* ap = p.tri_attr + ((size_t)f * p.tri_cap + slot) * NQ;
                 float rgb[3];
                 shade_fragment<SHADER>(wt.fu, ap, w0, w1, w2, q.diffuse, q.normal, sh, rgb);
                 col = (col & 0xFF000000u) | colour_bytes(rgb); /* alpha is never written: renderbuffer.cpp:38-44 */
-                if (q.primid && f == 0) q.primid[(size_t)py * p.W + px] = __float_as_uint(r2.w);
+                if (q.primid && f == 0) q.primid[(size_t)py * p.W + px] = __float_as_uint(__ldg(frame_rec + (size_t)slot * 4 + 2).w);
             }
-            if (q.pixels_covered) covered_acc += __popc(__ballot_sync(FULL, j != ORD_NONE));
+            if (q.pixels_covered) covered_acc += __popc(__ballot_sync(FULL, slot != ORD_NONE));
             if (tma) {
                 wt.color[pix] = col;
             } else if (in_frame) {
-                if (MODE == MODE_CLEAR_FOLD || j != ORD_NONE) {
+                if (MODE == MODE_CLEAR_FOLD || slot != ORD_NONE) {
                     const size_t o = (size_t)f * q.frame_stride + (size_t)py * p.W + px;
                     q.color[o] = col;
                     q.depth[o] = wt.depth[pix];
