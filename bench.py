@@ -31,7 +31,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 W, H = 1920, 1080
-FRAMES_PER_STEP = 128
+FRAMES_PER_STEP = 256
 ORBIT = 1024
 SCENE = "african_head"
 # dram__bytes_read.sum + dram__bytes_write.sum of one raster_main launch (128 frames) in the committed ncu --set full

@@ -787,9 +787,13 @@ __global__ void __launch_bounds__(RW_THREADS, ShaderAttrs<SHADER>::LIT ? HANA_OC
                                         const float4 r3 = wt.tri[j * RW_REC_Q + 3]; /* d0, d1, d2, 1/uz */
                                         const f2 RUZ = f2_dup(r3.w), NUZ = f2_dup(-r1.z);
                                         /* (1 - (u.x+u.y)/u.z, u.y/u.z, u.x/u.z): graphics.cpp:231 */
-                                        const f2 W0 = f2_fma(f2_div_by_recip(S, NUZ, RUZ), f2_negone(), f2_one());
-                                        f2 W1 = f2_div_by_recip(UY, NUZ, RUZ);
-                                        f2 W2 = f2_div_by_recip(UX, NUZ, RUZ);
+                                        /* three independent Markstein quotients (f2_div_by_recip), interleaved */
+                                        const f2 qs0 = f2_mul(S, RUZ), qy0 = f2_mul(UY, RUZ), qx0 = f2_mul(UX, RUZ);
+                                        const f2 rs = f2_fma(qs0, NUZ, S), ry = f2_fma(qy0, NUZ, UY), rx = f2_fma(qx0, NUZ, UX);
+                                        const f2 qs = f2_fma(rs, RUZ, qs0);
+                                        f2 W1 = f2_fma(ry, RUZ, qy0);
+                                        f2 W2 = f2_fma(rx, RUZ, qx0);
+                                        const f2 W0 = f2_fma(qs, f2_negone(), f2_one());
                                         if (r4.z != 0.f) { /* B and C were exchanged: so were u.x and u.y */
                                             const f2 t = W1;
                                             W1 = W2;
