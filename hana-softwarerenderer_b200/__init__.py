@@ -35,6 +35,8 @@ from .api import (  # noqa: F401
     tga_write,
     PRESENT_BGRA8,
     PRESENT_BGR8,
+    PASS_SHADOW,
+    PASS_MAIN,
 )
 from . import scene, sharding  # noqa: F401
 from .scene import (  # noqa: F401

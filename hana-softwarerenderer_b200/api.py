@@ -132,6 +132,9 @@ def load():
         "hana_sweep_checksums": [vp, i, vp],
         "hana_sweep_stats": [vp, i, vp],
         "hana_sweep_present": [vp, i, i, i, vp, C.POINTER(vp)],
+        "hana_sweep_set_bands": [vp, i, i, i, i],
+        "hana_sweep_render_pass": [vp, i, vp, i, vp, i, vp, vp, vp, f],
+        "hana_sweep_shadow_ptrs": [vp, C.POINTER(vp), C.POINTER(i), C.POINTER(C.c_size_t)],
         "hana_tga_write": [C.c_char_p, vp, i, i, i, i],
         "hana_obj_load": [C.c_char_p, i, C.POINTER(vp), C.POINTER(i)],
         "hana_tga_load": [C.c_char_p, i, C.POINTER(vp), C.POINTER(i), C.POINTER(i), C.POINTER(i)],
@@ -396,6 +399,31 @@ class Sweep:
         _ck(self.ctx.L.hana_sweep_render_dev(self.h, model.h, shader, dev, int(bool(enable_shadow)), n_frames, _h(diffuse),
                                              _h(normal), clr, float(clear_depth)))
 
+    # -- one frame split by screen tiles over several GPUs --
+    def set_bands(self, shadow=(0, 0), main=(0, 0)):
+        """Tile rows (first, count) of the shadow / main pass this sweep renders; count 0 = all rows."""
+        _ck(self.ctx.L.hana_sweep_set_bands(self.h, int(shadow[0]), int(shadow[1]), int(main[0]), int(main[1])))
+
+    def render_pass(self, which, model, shader, uniforms, diffuse=None, normal=None, clear_rgba=(0, 0, 0, 1),
+                    clear_depth=FLT_MAX):
+        """ONE pass of DrawModel::draw (PASS_SHADOW: scene.h:86, PASS_MAIN: scene.h:91) over this sweep's band."""
+        arr = uniforms if isinstance(uniforms, C.Array) else self.pack_uniforms(uniforms)
+        clr = (C.c_uint8 * 4)(*clear_rgba)
+        _ck(self.ctx.L.hana_sweep_render_pass(self.h, int(which), model.h, shader, arr, len(arr), _h(diffuse), _h(normal), clr,
+                                              float(clear_depth)))
+
+    def device_planes(self):
+        """(colour ptr, depth ptr, frame stride in pixels) of the frame ring; synchronises."""
+        c, d, st = C.c_void_p(), C.c_void_p(), C.c_size_t()
+        _ck(self.ctx.L.hana_sweep_device_ptrs(self.h, C.byref(c), C.byref(d), C.byref(st)))
+        return c.value, d.value, st.value
+
+    def shadow_plane(self):
+        """(ptr, pitch in bytes, frame stride in bytes) of the 1-byte shadow maps; synchronises."""
+        p, pitch, st = C.c_void_p(), C.c_int(), C.c_size_t()
+        _ck(self.ctx.L.hana_sweep_shadow_ptrs(self.h, C.byref(p), C.byref(pitch), C.byref(st)))
+        return p.value, pitch.value, st.value
+
     def download(self, frame):
         color = np.empty((self.height, self.width, 4), np.uint8)
         depth = np.empty((self.height, self.width), np.float32)
@@ -447,6 +475,7 @@ def frame_checksum(color, depth):
 
 
 PRESENT_BGRA8, PRESENT_BGR8 = 0, 1
+PASS_SHADOW, PASS_MAIN = 1, 2
 
 
 def obj_load(path, normal_pass=1):

@@ -153,6 +153,7 @@ struct hana_sweep {
     uint32_t* tri_counts_pin;      /* pinned host: [2][max_frames] */
     cudaEvent_t ev_render, ev_copy;
     bool copy_in_flight;
+    int band[2][2];                /* tile rows [first, first+count) of the shadow / main pass; count 0 = all (hana_sweep_set_bands) */
     uint8_t* present_buf;          /* device: presented frames (hana_sweep_present) */
     size_t present_cap;
     struct Pending {
@@ -618,6 +619,7 @@ struct PassDesc {
     /* split passes (lazy only): phase 1 = setup + scan + fill on `stream` with scratch set `scratch`, phase 2 = raster */
     int phase = 0;
     int scratch = 0;
+    int band_first = 0, band_count = 0; /* tile rows of a split frame; count 0 = the whole frame */
     cudaStream_t stream = nullptr;
 };
 
@@ -724,6 +726,8 @@ static int run_pass(hana_ctx* ctx, const PassDesc& d) {
         p.tiles_x = tiles_x;
         p.tiles_y = tiles_y;
         p.n_tiles = (int)n_tiles;
+        p.band_y0 = d.band_count > 0 ? std::min(d.band_first, tiles_y) : 0;
+        p.band_y1 = d.band_count > 0 ? std::min(d.band_first + d.band_count, tiles_y) : tiles_y;
         p.uniforms = d.uniforms;
         p.tri_rec = sc.tri_rec;
         p.tri_attr = sc.tri_attr;
@@ -1025,6 +1029,7 @@ extern "C" int hana_sweep_create(hana_ctx* ctx, int width, int height, int max_f
     s->max_frames = max_frames;
     s->last_frames = 0;
     s->last_clear_depth = 0.f;
+    memset(s->band, 0, sizeof(s->band));
     memset(&s->last_stats, 0, sizeof(s->last_stats));
     size_t n = (size_t)width * height;
     s->shadow_pitch = (width + 15) / 16 * 16;
@@ -1083,14 +1088,15 @@ extern "C" int hana_sweep_destroy(hana_sweep* s) {
 }
 
 /* Both passes of every frame of the batch (scene.h:73-91). lazy: launch everything without reading anything back. */
+enum { SWEEP_PASS_SHADOW = 1, SWEEP_PASS_MAIN = 2, SWEEP_PASS_BOTH = 3 };
 static int sweep_render_passes(hana_sweep* s, const hana_model* model, int shader_id, int enable_shadow, int n_frames,
                                const hana_texture* diffuse, const hana_texture* normal, const uint8_t clear_rgba[4],
-                               float clear_depth, bool lazy) {
+                               float clear_depth, bool lazy, int passes = SWEEP_PASS_BOTH) {
     hana_ctx* ctx = s->ctx;
     PassCounters cnt[2];
     memset(cnt, 0, sizeof(cnt));
     PassDesc shadow_desc;
-    if (enable_shadow) { /* scene.h:73-88, into the internal R8 maps */
+    if (enable_shadow && (passes & SWEEP_PASS_SHADOW)) { /* scene.h:73-88, into the internal R8 maps */
         PassDesc d;
         d.shader = HANA_SHADER_SHADOW;
         d.mode = MODE_SHADOW_R8;
@@ -1114,6 +1120,8 @@ static int sweep_render_passes(hana_sweep* s, const hana_model* model, int shade
         d.counters_pinned = &s->pin->counters[0];
         d.tri_cap_used = &s->pending.tri_cap;
         d.pool_cap_used = &s->pending.pool_cap;
+        d.band_first = s->band[0][0];
+        d.band_count = s->band[0][1];
         if (lazy) { /* fork: the main pass is binned on the side stream while this one is binned here */
             CU_TRY(cudaEventRecord(ctx->ev_fork, ctx->stream));
             CU_TRY(cudaStreamWaitEvent(ctx->side_stream, ctx->ev_fork, 0));
@@ -1122,8 +1130,14 @@ static int sweep_render_passes(hana_sweep* s, const hana_model* model, int shade
         HANA_TRY(run_pass(ctx, d));
         shadow_desc = d;
     }
+    if (!(passes & SWEEP_PASS_MAIN)) {
+        s->last_frames = n_frames;
+        return HANA_OK;
+    }
     PassDesc d;
     d.shader = shader_id;
+    d.band_first = s->band[1][0];
+    d.band_count = s->band[1][1];
     d.mode = MODE_CLEAR_FOLD;
     d.n_frames = n_frames;
     d.W = s->w;
@@ -1272,6 +1286,56 @@ extern "C" int hana_sweep_render_dev(hana_sweep* s, const hana_model* model, int
 extern "C" int hana_sweep_uniforms_dev(hana_sweep* s, void** out) {
     if (!s || !out) return fail(HANA_E_INVALID, "NULL argument");
     *out = s->u_raw;
+    return HANA_OK;
+}
+
+/* ---- single frame split by screen tiles over several GPUs ---------------------------------------
+ * Each GPU owns a band of tile rows per pass. Pass 1 leaves this GPU's band of the R8 shadow maps in HBM; the caller
+ * exchanges the bands (the maps of all GPUs must be complete before any pass-2 fragment is shaded: IShader.h:124 looks
+ * up arbitrary light-space texels), then pass 2 renders this GPU's band of the frame. The exchange itself is the
+ * launcher's (sharding.py: NCCL all-gather over NVLink): this library has no inter-process state. */
+extern "C" int hana_sweep_set_bands(hana_sweep* s, int shadow_row_first, int shadow_row_count, int main_row_first,
+                                    int main_row_count) {
+    if (!s) return fail(HANA_E_INVALID, "sweep is NULL");
+    if (shadow_row_first < 0 || shadow_row_count < 0 || main_row_first < 0 || main_row_count < 0)
+        return fail(HANA_E_INVALID, "negative tile row range");
+    s->band[0][0] = shadow_row_first;
+    s->band[0][1] = shadow_row_count;
+    s->band[1][0] = main_row_first;
+    s->band[1][1] = main_row_count;
+    return HANA_OK;
+}
+
+extern "C" int hana_sweep_render_pass(hana_sweep* s, int pass, const hana_model* model, int shader_id,
+                                      const HanaUniforms* uniforms, int n_frames, const hana_texture* diffuse,
+                                      const hana_texture* normal, const uint8_t clear_rgba[4], float clear_depth) {
+    if (!s) return fail(HANA_E_INVALID, "sweep is NULL");
+    if (pass != HANA_PASS_SHADOW && pass != HANA_PASS_MAIN) return fail(HANA_E_INVALID, "pass is HANA_PASS_SHADOW or HANA_PASS_MAIN");
+    HANA_TRY(check_draw_args(s->ctx, model, uniforms, pass == HANA_PASS_SHADOW ? HANA_SHADER_SHADOW : shader_id));
+    if (!clear_rgba) return fail(HANA_E_INVALID, "clear_rgba is NULL");
+    if (n_frames < 1 || n_frames > s->max_frames) return fail(HANA_E_INVALID, "n_frames outside 1..max_frames");
+    hana_ctx* ctx = s->ctx;
+    HANA_TRY(use_device(ctx));
+    HANA_TRY(sweep_verify(s));
+    s->pending.active = false;
+    if (s->copy_in_flight) {
+        CU_TRY(cudaStreamWaitEvent(ctx->stream, s->ev_copy, 0));
+        s->copy_in_flight = false;
+    }
+    HANA_TRY(upload_uniforms(ctx, uniforms, n_frames, s->u_raw, s->u_dev));
+    /* with read-backs (not lazy): a split frame is one large frame, not a stream of small ones */
+    return sweep_render_passes(s, model, shader_id, uniforms[0].enable_shadow != 0, n_frames, diffuse, normal, clear_rgba, clear_depth,
+                               false, pass == HANA_PASS_SHADOW ? SWEEP_PASS_SHADOW : SWEEP_PASS_MAIN);
+}
+
+extern "C" int hana_sweep_shadow_ptrs(hana_sweep* s, void** r8_dev, int* pitch_bytes, size_t* frame_stride_bytes) {
+    if (!s) return fail(HANA_E_INVALID, "sweep is NULL");
+    HANA_TRY(use_device(s->ctx));
+    HANA_TRY(sweep_verify(s));
+    CU_TRY(cudaStreamSynchronize(s->ctx->stream));
+    if (r8_dev) *r8_dev = s->shadow_r8;
+    if (pitch_bytes) *pitch_bytes = s->shadow_pitch;
+    if (frame_stride_bytes) *frame_stride_bytes = s->shadow_frame_bytes;
     return HANA_OK;
 }
 

@@ -71,6 +71,7 @@ struct PassParams {
     int nfaces;
     int n_frames;
     int W, H, tiles_x, tiles_y, n_tiles;
+    int band_y0, band_y1; /* tile rows [band_y0, band_y1) this pass renders: the whole frame, or one GPU's band of a split frame */
     const DevUniforms* uniforms; /* [n_frames] */
     /* scratch */
     float4* tri_rec;      /* [n_frames][tri_cap][4]: raster records */
@@ -221,7 +222,7 @@ __device__ __forceinline__ void store_triangle(const PassParams& p, int f, uint3
 
 __device__ __forceinline__ void count_tiles(const PassParams& p, int f, const TriRecord& r) {
     int tx0 = (int)(r.bbx & 0xFFFFu) >> 4, tx1 = (int)(r.bbx >> 16) >> 4;
-    int ty0 = (int)(r.bby & 0xFFFFu) >> 4, ty1 = (int)(r.bby >> 16) >> 4;
+    const int ty0 = max((int)(r.bby & 0xFFFFu) >> 4, p.band_y0), ty1 = min((int)(r.bby >> 16) >> 4, p.band_y1 - 1);
     uint32_t* tc = p.tile_count + (size_t)f * p.tile_pad;
     for (int ty = ty0; ty <= ty1; ty++)
         for (int tx = tx0; tx <= tx1; tx++) atomicAdd(tc + tile_slot(p, ty * p.tiles_x + tx), 1u);
@@ -396,9 +397,9 @@ __global__ void __launch_bounds__(256) fill_kernel(PassParams p) {
         const float4 q2 = __ldg(warp_rec + lane * 4 + 2);
         const uint32_t bbx = __float_as_uint(q2.x), bby = __float_as_uint(q2.y);
         tx0 = (int)(bbx & 0xFFFFu) >> 4;
-        ty0 = (int)(bby & 0xFFFFu) >> 4;
+        ty0 = max((int)(bby & 0xFFFFu) >> 4, p.band_y0);
         ntx = ((int)(bbx >> 16) >> 4) - tx0 + 1;
-        nt = ntx * (((int)(bby >> 16) >> 4) - ty0 + 1);
+        nt = ntx * max(min((int)(bby >> 16) >> 4, p.band_y1 - 1) - ty0 + 1, 0);
     }
     int incl = nt;
 #pragma unroll
@@ -508,8 +509,8 @@ __device__ __forceinline__ void clear_slots(const RasterParams& q, RasterSmem<MO
     const PassParams& p = q.p;
     const uint32_t s = base + (threadIdx.x & 31u);
     const int f = (int)(s / (uint32_t)p.n_tiles), t = (int)(s % (uint32_t)p.n_tiles);
-    if (s < n_slots && p.tile_count[(size_t)f * p.tile_pad + tile_slot(p, t)] == 0u) {
-        const int tx = t % p.tiles_x, ty = t / p.tiles_x;
+    const int tx = t % p.tiles_x, ty = t / p.tiles_x;
+    if (s < n_slots && ty >= p.band_y0 && ty < p.band_y1 && p.tile_count[(size_t)f * p.tile_pad + tile_slot(p, t)] == 0u) {
         if (q.use_tma) {
             if (MODE == MODE_SHADOW_R8) {
                 tma_store_3d(&tm_r8, sm.clr_r8, tx * TILE, ty * TILE, f);

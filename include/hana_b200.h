@@ -248,6 +248,28 @@ HANA_API int hana_sweep_device_ptrs(hana_sweep* s, void** color_dev, void** dept
 HANA_API int hana_sweep_checksums(hana_sweep* s, int n_frames, uint64_t* out_host);
 HANA_API int hana_sweep_stats(hana_sweep* s, int frame, HanaStats* out); /* synchronises */
 
+/* --- one frame split by screen tiles over several GPUs (BASELINE.json north_star, optional mode) --
+ * The frame's 16x16 tiles are dealt to the GPUs in bands of tile rows. Geometry is replicated; each GPU rasterises
+ * only the tiles of its band, per pass. Replaces nothing in the reference (it has one thread); the per-GPU work is
+ * still graphics_draw_triangle (graphics.cpp:378-407) restricted to a pixel range.
+ *   hana_sweep_set_bands   tile rows [first, first+count) of the shadow pass / of the main pass this sweep renders
+ *                          from now on; count 0 = every row (the default).
+ *   hana_sweep_render_pass ONE pass of DrawModel::draw (scene.h:86 or :91) for n_frames frames: HANA_PASS_SHADOW
+ *                          leaves this GPU's band of the 1-byte shadow maps in HBM, HANA_PASS_MAIN shades its band of
+ *                          the frames from whatever the maps hold. Between the two the caller makes the maps complete
+ *                          on every GPU (NCCL all-gather of the bands: sharding.py) — pass 2 looks up arbitrary
+ *                          light-space texels (IShader.h:107-129), so that exchange is a real data dependency.
+ *   hana_sweep_shadow_ptrs the maps' device memory: texel (x,y) of frame f at r8[f*frame_stride + y*pitch + x].
+ * A band of tile rows is a contiguous byte range of every plane (rows are row-major, y up), so bands gather in place. */
+#define HANA_PASS_SHADOW 1
+#define HANA_PASS_MAIN 2
+HANA_API int hana_sweep_set_bands(hana_sweep* s, int shadow_row_first, int shadow_row_count, int main_row_first,
+                         int main_row_count);
+HANA_API int hana_sweep_render_pass(hana_sweep* s, int pass, const hana_model* model, int shader_id,
+                           const HanaUniforms* uniforms, int n_frames, const hana_texture* diffuse,
+                           const hana_texture* normal, const uint8_t clear_rgba[4], float clear_depth);
+HANA_API int hana_sweep_shadow_ptrs(hana_sweep* s, void** r8_dev, int* pitch_bytes, size_t* frame_stride_bytes);
+
 /* --- present / output ------------------------------------ */
 /* Replaces window_draw_buffer's conversion loop (win32.cpp:348-370): frames [first, first+count) of the last batch
  * as top-down B,G,R,255 (BGRA8) or B,G,R (BGR8, a TGA payload) surfaces, converted on the device; copied to dst_host
