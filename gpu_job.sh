@@ -1,6 +1,12 @@
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
-nvidia-smi -L | head -3
 ( timeout 900 python -m pytest tests -x -q -m gpu 2>&1 | tail -6 ) 2>&1
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29611 tools/split_frame.py --reps 5 > gpurun_out/split_n2.json 2> gpurun_out/split_n2.err; tail -3 gpurun_out/split_n2.err; cat gpurun_out/split_n2.json
-timeout 600 python tools/split_frame.py --reps 5 > gpurun_out/split_n1.json 2> gpurun_out/split_n1.err; cat gpurun_out/split_n1.json
+timeout 600 python bench.py --no-cpu-baseline > gpurun_out/bench_p4.json 2> gpurun_out/bench_p4.err; tail -3 gpurun_out/bench_p4.err
+python - <<'PY'
+import json
+for n in ('bench_p4',):
+    try:
+        d=json.load(open('gpurun_out/%s.json'%n))
+        print(n, round(d['value']), round(d['us_per_frame'],2), 'e2e', round(d['e2e']['value']), {k: round(v,3) for k,v in d['kernel_ms_per_step'].items()}, 'ms/step', round(d['ms_per_step'],3), d['roofline']['frac'], d['frame_roofline']['frac'])
+    except Exception as e: print(n, 'failed', e)
+PY

@@ -200,9 +200,16 @@ __device__ __forceinline__ void store_triangle(const PassParams& p, int f, uint3
 #pragma unroll
     for (int k = 0; k < NA; k++) {
         const int src = shader_attr_src(SHADER, k);
-        a[3 * k + 0] = v0[src];
-        a[3 * k + 1] = v1[src];
-        a[3 * k + 2] = v2[src];
+        if (ShaderAttrs<SHADER>::LIT) { /* pairwise: (v0.a, v0.b, v1.a, v1.b, v2.a, v2.b) per attribute pair (interp_lit_packed) */
+            const int b = 6 * (k >> 1) + (k & 1);
+            a[b] = v0[src];
+            a[b + 2] = v1[src];
+            a[b + 4] = v2[src];
+        } else {
+            a[3 * k + 0] = v0[src];
+            a[3 * k + 1] = v1[src];
+            a[3 * k + 2] = v2[src];
+        }
     }
 #pragma unroll
     for (int k = 3 * NA; k < (NQ - 1) * 4; k++) a[k] = 0.f;
@@ -565,6 +572,11 @@ __device__ __forceinline__ bool shade_fragment_t(const FragUniforms& fu, const f
     constexpr int NQ = ShaderAttrs<SHADER>::NQ;
     bool bad = false;
     bool* pb = FAST ? &bad : nullptr;
+    if (ShaderAttrs<SHADER>::LIT) {
+        const LitAttrs la = interp_lit_packed(ap, w0, w1, w2, pb);
+        fragment_lit_packed<SHADER>(fu, la, diffuse, normal, sh, rgb, pb);
+        return bad;
+    }
     const float4 rw = __ldg(ap);
     VaryingWeights vw = varying_weights(w0, w1, w2, rw.x, rw.y, rw.z, pb);
     float a[(NQ - 1) * 4];
