@@ -24,6 +24,7 @@
 #define HANA_KERNELS_CUH
 
 #include <cuda.h>
+#include <type_traits>
 #include <cuda_runtime.h>
 
 #include "hana_core.cuh"
@@ -452,12 +453,14 @@ __global__ void __launch_bounds__(256) fill_kernel(PassParams p) {
  * range meets, so the triangle loop is warp-uniform and skips rows of sub-blocks without a per-pixel
  * instruction.
  *
- * Arithmetic is packed two pixels at a time (hana_pack.cuh): the two pixels of a lane that share a row
- * (column halves 0 and 1) go through every multiply / add of graphics.cpp:222-233 and :186-194 as the two
- * halves of one FFMA2, with the record's scalars as broadcast operands. Per record: 3 packed operations
- * for the x-dependent terms, 3 per pair of rows for the y-dependent ones, then 5 per row of 64 pixels and
- * one 3-input max + one compare per pixel for the inside test; covered pixels take 14 more packed
- * operations for the exact weights and the depth. The (min depth, max key) resolve lives in registers as
+ * Arithmetic is packed two pixels at a time (hana_pack.cuh): the two pixels of a lane that share a column
+ * half and sit in row quarters 2k and 2k+1 go through every multiply / add of graphics.cpp:222-233 and
+ * :186-194 as the two halves of one FFMA2, with the record's scalars as broadcast operands, so one
+ * instruction covers an 8x8 block of the tile (pairing the two column halves of a row instead, 16x4 pixels per
+ * instruction, measured 6 % slower in the shadow pass: small triangles leave more of a long thin block
+ * empty). Per record: 3 packed operations for the x-dependent terms, 3 per pair of row quarters for the
+ * y-dependent ones, then 5 per 8x8 block and one 3-input max + one compare per pixel for the inside test;
+ * covered pixels take 14 more packed operations for the exact weights and the depth. The (min depth, max key) resolve lives in registers as
  * {depth, triangle slot} per pixel; the three weights of a fragment that wins are parked in shared memory
  * (they cost three stores where the fragment wins, which happens ~1.01 times per visible pixel), so the
  * shading stage neither re-fetches a record nor recomputes a weight. The warp's tile is flushed with TMA
@@ -474,6 +477,13 @@ constexpr int RW_WARPS = 4;
 #endif
 #ifndef HANA_OCC_OTHER
 #define HANA_OCC_OTHER 7
+#endif
+#ifndef HANA_SHADE_UNROLL
+#define HANA_SHADE_UNROLL 1 /* sub-blocks shaded per iteration of the shading loop */
+#endif
+constexpr int SHADE_UNROLL = HANA_SHADE_UNROLL;
+#ifndef HANA_PREFETCH
+#define HANA_PREFETCH 0
 #endif
 constexpr int RW_THREADS = RW_WARPS * 32;
 constexpr int RW_CHUNK = 32;
@@ -761,11 +771,101 @@ __global__ void __launch_bounds__(RW_THREADS, ShaderAttrs<SHADER>::LIT ? HANA_OC
                 }
             }
             __syncwarp();
+#if HANA_PREFETCH
+            if (c0 == 0) { /* the next tile's entry (requested before this tile's records) has arrived by now: pull its
+                              first records towards the SM while this tile is processed */
+                const uint32_t nx_item = __shfl_sync(FULL, e_nxt.x, 0), nx_cnt = __shfl_sync(FULL, e_nxt.y, 0);
+                const uint32_t nx_off = __shfl_sync(FULL, e_nxt.z, 0);
+                if (nx_item != WORK_INVALID && lane < min(nx_cnt, (uint32_t)RW_CHUNK)) {
+                    const float4* nx = p.tile_recs + ((size_t)nx_off + lane) * 4;
+                    asm volatile("prefetch.global.L1 [%0];" ::"l"(nx));
+                }
+            }
+#endif
             for (int j = 0; j < n; j++) {
                 const float4 r0 = wt.tri[j * RW_REC_Q + 0]; /* ax, ay, s0x, s0y */
                 const float4 r1 = wt.tri[j * RW_REC_Q + 1]; /* s1x, s1y, uz, thr */
                 const float4 r4 = wt.tri[j * RW_REC_Q + 4]; /* slot, key, exchanged, mask */
                 const uint32_t m = __float_as_uint(r4.w);
+                /* Two pixels of the lane, A and B (state indices ia, ib; coordinates (fxA, fyA), (fxB, fyB); shared-memory
+                 * pixel indices pixA, pixB), whose u.x and u.y arrive as the halves of UX and UY. */
+                auto pixel_pair = [&](const f2 UX, const f2 UY, auto ia_, auto ib_, const float fxA, const float fxB, const float fyA,
+                                      const float fyB, const int pixA, const int pixB) {
+                    constexpr int ia = decltype(ia_)::value, ib = decltype(ib_)::value;
+                    const f2 S = f2_add(UX, UY);
+                    const f2 D = f2_sub(S, f2_dup(r1.z));
+                    const f2 E = f2_sub(f2_dup(-r1.w), D);
+                    /* coverage_test() for u.z < 0: u.x <= 0, u.y <= 0, d >= -thr */
+                    const bool cA = fmax3(f2_lo(UX), f2_lo(UY), f2_lo(E)) <= 0.f;
+                    const bool cB = fmax3(f2_hi(UX), f2_hi(UY), f2_hi(E)) <= 0.f;
+                    if (cA || cB) {
+                        /* the reference only visits pixels of its clamped bounding box: graphics.cpp:339-351 */
+                        const float4 r2 = wt.tri[j * RW_REC_Q + 2];
+                        const bool inA = cA && fabsf(fyA - r2.y) <= r2.w && fabsf(fxA - r2.x) <= r2.z;
+                        const bool inB = cB && fabsf(fyB - r2.y) <= r2.w && fabsf(fxB - r2.x) <= r2.z;
+                        if (inA || inB) {
+                            const float4 r3 = wt.tri[j * RW_REC_Q + 3]; /* d0, d1, d2, 1/uz */
+                            const f2 RUZ = f2_dup(r3.w), NUZ = f2_dup(-r1.z);
+                            /* (1 - (u.x+u.y)/u.z, u.y/u.z, u.x/u.z): graphics.cpp:231; three independent Markstein
+                             * quotients (f2_div_by_recip), written interleaved */
+                            const f2 qs0 = f2_mul(S, RUZ), qy0 = f2_mul(UY, RUZ), qx0 = f2_mul(UX, RUZ);
+                            const f2 rs = f2_fma(qs0, NUZ, S), ry = f2_fma(qy0, NUZ, UY), rx = f2_fma(qx0, NUZ, UX);
+                            const f2 qs = f2_fma(rs, RUZ, qs0);
+                            f2 W1 = f2_fma(ry, RUZ, qy0);
+                            f2 W2 = f2_fma(rx, RUZ, qx0);
+                            const f2 W0 = f2_fma(qs, f2_negone(), f2_one());
+                            if (r4.z != 0.f) { /* B and C were exchanged: so were u.x and u.y */
+                                const f2 t = W1;
+                                W1 = W2;
+                                W2 = t;
+                            }
+                            /* interpolate_depth graphics.cpp:186-194 */
+                            f2 Z = f2_mul_from_zero(f2_dup(r3.z), W2);
+                            Z = f2_add(Z, f2_mul(f2_dup(r3.y), W1));
+                            Z = f2_add(Z, f2_mul(f2_dup(r3.x), W0));
+                            const uint32_t slot = __float_as_uint(r4.x);
+                            const float zA = f2_lo(Z), zB = f2_hi(Z);
+                            bool winA = inA && zA < bz[ia], winB = inB && zB < bz[ib];
+                            const bool tieA = inA && zA == bz[ia], tieB = inB && zB == bz[ib];
+                            if (tieA || tieB) { /* rare */
+                                const uint32_t key = __float_as_uint(r4.y);
+                                if (tieA) winA = wins_tie(ia, key);
+                                if (tieB) winB = wins_tie(ib, key);
+                            }
+                            if (winA) {
+                                bz[ia] = zA;
+                                bj[ia] = slot;
+                            }
+                            if (winB) {
+                                bz[ib] = zB;
+                                bj[ib] = slot;
+                            }
+                            if (INLOOP) {
+                                if (winA || winB) { /* ShadowShader::fragment IShader.cpp:176-180 on the winning fragments */
+                                    const float4 rw = wt.sattr[j * 2], a = wt.sattr[j * 2 + 1];
+                                    /* interpolate_varyings graphics.cpp:205-220 for clip_pos.z */
+                                    const f2 V0 = f2_mul(f2_dup(rw.x), W0), V1 = f2_mul(f2_dup(rw.y), W1), V2 = f2_mul(f2_dup(rw.z), W2);
+                                    const f2 SUM = f2_add(f2_add(V0, V1), V2);
+                                    const f2 NORM = f2_rcp(SUM);
+                                    const f2 AT = f2_mul(f2_add(f2_add(f2_mul(f2_dup(a.x), V0), f2_mul(f2_dup(a.y), V1)), f2_mul(f2_dup(a.z), V2)), NORM);
+                                    if (winA) bj[ia] |= shadow_byte(f2_lo(AT)) << 24;
+                                    if (winB) bj[ib] |= shadow_byte(f2_hi(AT)) << 24;
+                                }
+                            } else {
+                                if (winA) {
+                                    pw0[pixA] = f2_lo(W0);
+                                    wt.pw1[pixA] = f2_lo(W1);
+                                    wt.pw2[pixA] = f2_lo(W2);
+                                }
+                                if (winB) {
+                                    pw0[pixB] = f2_hi(W0);
+                                    wt.pw1[pixB] = f2_hi(W1);
+                                    wt.pw2[pixB] = f2_hi(W2);
+                                }
+                            }
+                        }
+                    }
+                };
                 /* x-dependent terms of cross(s0, s1) for both column halves: graphics.cpp:224-229 */
                 const f2 S0Z = f2_sub(f2_dup(r0.x), FPX);          /* A.x - P.x */
                 const f2 T2 = f2_mul(S0Z, f2_dup(r1.y));           /* s0.z * s1.y */
@@ -774,91 +874,22 @@ __global__ void __launch_bounds__(RW_THREADS, ShaderAttrs<SHADER>::LIT ? HANA_OC
                 for (int rp = 0; rp < 2; rp++) {
                     if (m & (0xFu << (4 * rp))) { /* warp-uniform */
                         /* y-dependent terms for two row quarters */
-                        const f2 S1Z = f2_sub(f2_dup(r0.y), rp ? FPY23 : FPY01); /* A.y - P.y */
-                        const f2 T1 = f2_mul(f2_dup(r0.w), S1Z);                  /* s0.y * s1.z */
-                        const f2 T4 = f2_mul(f2_dup(r0.z), S1Z);                  /* s0.x * s1.z */
+                        const f2 FPY = rp ? FPY23 : FPY01;
+                        const f2 S1Z = f2_sub(f2_dup(r0.y), FPY); /* A.y - P.y */
+                        const f2 T1 = f2_mul(f2_dup(r0.w), S1Z);  /* s0.y * s1.z */
+                        const f2 T4 = f2_mul(f2_dup(r0.z), S1Z);  /* s0.x * s1.z */
 #pragma unroll
                         for (int h = 0; h < 2; h++) {
-                            const int r = rp * 2 + h;
-                            if (m & (3u << (2 * r))) { /* warp-uniform */
-                                const f2 UX = f2_sub(f2_dup(f2_half(T1, h)), T2);
-                                const f2 UY = f2_sub(T3, f2_dup(f2_half(T4, h)));
-                                const f2 S = f2_add(UX, UY);
-                                const f2 D = f2_sub(S, f2_dup(r1.z));
-                                const f2 E = f2_sub(f2_dup(-r1.w), D);
-                                /* coverage_test() for u.z < 0: u.x <= 0, u.y <= 0, d >= -thr */
-                                const bool cA = fmax3(f2_lo(UX), f2_lo(UY), f2_lo(E)) <= 0.f;
-                                const bool cB = fmax3(f2_hi(UX), f2_hi(UY), f2_hi(E)) <= 0.f;
-                                if (cA || cB) {
-                                    /* the reference only visits pixels of its clamped bounding box: graphics.cpp:339-351 */
-                                    const float4 r2 = wt.tri[j * RW_REC_Q + 2];
-                                    const float fpy = f2_half(rp ? FPY23 : FPY01, h);
-                                    const bool rowin = fabsf(fpy - r2.y) <= r2.w;
-                                    const bool inA = cA && rowin && fabsf(f2_lo(FPX) - r2.x) <= r2.z;
-                                    const bool inB = cB && rowin && fabsf(f2_hi(FPX) - r2.x) <= r2.z;
-                                    if (inA || inB) {
-                                        const float4 r3 = wt.tri[j * RW_REC_Q + 3]; /* d0, d1, d2, 1/uz */
-                                        const f2 RUZ = f2_dup(r3.w), NUZ = f2_dup(-r1.z);
-                                        /* (1 - (u.x+u.y)/u.z, u.y/u.z, u.x/u.z): graphics.cpp:231 */
-                                        /* three independent Markstein quotients (f2_div_by_recip), interleaved */
-                                        const f2 qs0 = f2_mul(S, RUZ), qy0 = f2_mul(UY, RUZ), qx0 = f2_mul(UX, RUZ);
-                                        const f2 rs = f2_fma(qs0, NUZ, S), ry = f2_fma(qy0, NUZ, UY), rx = f2_fma(qx0, NUZ, UX);
-                                        const f2 qs = f2_fma(rs, RUZ, qs0);
-                                        f2 W1 = f2_fma(ry, RUZ, qy0);
-                                        f2 W2 = f2_fma(rx, RUZ, qx0);
-                                        const f2 W0 = f2_fma(qs, f2_negone(), f2_one());
-                                        if (r4.z != 0.f) { /* B and C were exchanged: so were u.x and u.y */
-                                            const f2 t = W1;
-                                            W1 = W2;
-                                            W2 = t;
-                                        }
-                                        /* interpolate_depth graphics.cpp:186-194 */
-                                        f2 Z = f2_mul_from_zero(f2_dup(r3.z), W2);
-                                        Z = f2_add(Z, f2_mul(f2_dup(r3.y), W1));
-                                        Z = f2_add(Z, f2_mul(f2_dup(r3.x), W0));
-                                        const uint32_t slot = __float_as_uint(r4.x);
-                                        const float zA = f2_lo(Z), zB = f2_hi(Z);
-                                        bool winA = inA && zA < bz[2 * r], winB = inB && zB < bz[2 * r + 1];
-                                        const bool tieA = inA && zA == bz[2 * r], tieB = inB && zB == bz[2 * r + 1];
-                                        if (tieA || tieB) { /* rare */
-                                            const uint32_t key = __float_as_uint(r4.y);
-                                            if (tieA) winA = wins_tie(2 * r, key);
-                                            if (tieB) winB = wins_tie(2 * r + 1, key);
-                                        }
-                                        if (winA) {
-                                            bz[2 * r] = zA;
-                                            bj[2 * r] = slot;
-                                        }
-                                        if (winB) {
-                                            bz[2 * r + 1] = zB;
-                                            bj[2 * r + 1] = slot;
-                                        }
-                                        if (INLOOP) {
-                                            if (winA || winB) { /* ShadowShader::fragment IShader.cpp:176-180 on the winning fragments */
-                                                const float4 rw = wt.sattr[j * 2], a = wt.sattr[j * 2 + 1];
-                                                /* interpolate_varyings graphics.cpp:205-220 for clip_pos.z */
-                                                const f2 V0 = f2_mul(f2_dup(rw.x), W0), V1 = f2_mul(f2_dup(rw.y), W1), V2 = f2_mul(f2_dup(rw.z), W2);
-                                                const f2 SUM = f2_add(f2_add(V0, V1), V2);
-                                                const f2 NORM = f2_rcp(SUM);
-                                                const f2 AT = f2_mul(f2_add(f2_add(f2_mul(f2_dup(a.x), V0), f2_mul(f2_dup(a.y), V1)), f2_mul(f2_dup(a.z), V2)), NORM);
-                                                if (winA) bj[2 * r] |= shadow_byte(f2_lo(AT)) << 24;
-                                                if (winB) bj[2 * r + 1] |= shadow_byte(f2_hi(AT)) << 24;
-                                            }
-                                        } else {
-                                            const int pix = pix0 + r * 64;
-                                            if (winA) {
-                                                pw0[pix] = f2_lo(W0);
-                                                wt.pw1[pix] = f2_lo(W1);
-                                                wt.pw2[pix] = f2_lo(W2);
-                                            }
-                                            if (winB) {
-                                                pw0[pix + 8] = f2_hi(W0);
-                                                wt.pw1[pix + 8] = f2_hi(W1);
-                                                wt.pw2[pix + 8] = f2_hi(W2);
-                                            }
-                                        }
-                                    }
-                                }
+                            /* h = column half; the pair is the lane's two pixels of that column in row quarters 2rp, 2rp+1:
+                             * an 8x8 block of the tile per instruction */
+                            if (m & (5u << (4 * rp + h))) { /* warp-uniform */
+                                const f2 UX = f2_sub(T1, f2_dup(f2_half(T2, h)));
+                                const f2 UY = f2_sub(f2_dup(f2_half(T3, h)), T4);
+                                const float fx = f2_half(FPX, h);
+                                if (rp == 0 && h == 0) pixel_pair(UX, UY, std::integral_constant<int, 0>(), std::integral_constant<int, 2>(), fx, fx, f2_lo(FPY), f2_hi(FPY), pix0, pix0 + 64);
+                                if (rp == 0 && h == 1) pixel_pair(UX, UY, std::integral_constant<int, 1>(), std::integral_constant<int, 3>(), fx, fx, f2_lo(FPY), f2_hi(FPY), pix0 + 8, pix0 + 72);
+                                if (rp == 1 && h == 0) pixel_pair(UX, UY, std::integral_constant<int, 4>(), std::integral_constant<int, 6>(), fx, fx, f2_lo(FPY), f2_hi(FPY), pix0 + 128, pix0 + 192);
+                                if (rp == 1 && h == 1) pixel_pair(UX, UY, std::integral_constant<int, 5>(), std::integral_constant<int, 7>(), fx, fx, f2_lo(FPY), f2_hi(FPY), pix0 + 136, pix0 + 200);
                             }
                         }
                     }
@@ -895,7 +926,7 @@ __global__ void __launch_bounds__(RW_THREADS, ShaderAttrs<SHADER>::LIT ? HANA_OC
         }
         DevShadow sh = q.shadow;
         if (sh.base) sh.base += (size_t)f * q.shadow_frame_stride;
-#pragma unroll 1
+#pragma unroll SHADE_UNROLL
         for (int sb = 0; sb < 8; sb++) {
             const int pix = pix0 + (sb >> 1) * 64 + (sb & 1) * 8;
             const int px = ipx0 + (sb & 1) * 8, py = ipy0 + (sb >> 1) * 4;
