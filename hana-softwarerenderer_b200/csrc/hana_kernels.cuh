@@ -232,8 +232,11 @@ __device__ __forceinline__ void count_tiles(const PassParams& p, int f, const Tr
     int tx0 = (int)(r.bbx & 0xFFFFu) >> 4, tx1 = (int)(r.bbx >> 16) >> 4;
     const int ty0 = max((int)(r.bby & 0xFFFFu) >> 4, p.band_y0), ty1 = min((int)(r.bby >> 16) >> 4, p.band_y1 - 1);
     uint32_t* tc = p.tile_count + (size_t)f * p.tile_pad;
+    const bool single = tx0 == tx1 && ty0 == ty1; /* a range inside one tile: the triangle touches it or covers nothing */
     for (int ty = ty0; ty <= ty1; ty++)
-        for (int tx = tx0; tx <= tx1; tx++) atomicAdd(tc + tile_slot(p, ty * p.tiles_x + tx), 1u);
+        for (int tx = tx0; tx <= tx1; tx++)
+            if (single || tile_may_touch(r.ax, r.ay, r.s0x, r.s0y, r.s1x, r.s1y, r.uz, r.thr, (float)(tx * TILE), (float)(ty * TILE)))
+                atomicAdd(tc + tile_slot(p, ty * p.tiles_x + tx), 1u);
 }
 
 /* Rare path: the face is not trivially accepted. Sutherland-Hodgman in local
@@ -430,17 +433,21 @@ __global__ void __launch_bounds__(256) fill_kernel(PassParams p) {
         }
         const int local = k - __shfl_sync(FULL, excl, j);
         const int jtx0 = __shfl_sync(FULL, tx0, j), jty0 = __shfl_sync(FULL, ty0, j), jntx = __shfl_sync(FULL, ntx, j);
+        const bool single = __shfl_sync(FULL, nt, j) == 1; /* same decision as count_tiles() */
         if (k < total) {
             const float4* rec = warp_rec + j * 4;
             const float4 q0 = __ldg(rec), q1 = __ldg(rec + 1), q2 = __ldg(rec + 2), q3 = __ldg(rec + 3);
             const int row = local / jntx;
-            const int t = (jty0 + row) * p.tiles_x + jtx0 + (local - row * jntx);
-            const uint32_t s = atomicAdd(cur + tile_slot(p, t), 1u);
-            float4* d = p.tile_recs + ((size_t)__ldg(to + t) + s) * 4;
-            d[0] = q0;
-            d[1] = q1;
-            d[2] = q2;
-            d[3] = q3;
+            const int tx = jtx0 + (local - row * jntx), ty = jty0 + row;
+            const int t = ty * p.tiles_x + tx;
+            if (single || tile_may_touch(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, (float)(tx * TILE), (float)(ty * TILE))) {
+                const uint32_t s = atomicAdd(cur + tile_slot(p, t), 1u);
+                float4* d = p.tile_recs + ((size_t)__ldg(to + t) + s) * 4;
+                d[0] = q0;
+                d[1] = q1;
+                d[2] = q2;
+                d[3] = q3;
+            }
         }
     }
 }
