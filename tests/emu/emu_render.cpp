@@ -50,6 +50,26 @@ int emu_coverage(const float* abc6, int W, int H, int px, int py, float* w3) {
     return in ? 1 : 0;
 }
 
+// Binning's conservative triangle/tile test against exhaustive coverage of the tile's 256 pixels: returns
+// (tile_may_touch ? 1 : 0) | (any pixel of the tile inside ? 2 : 0). 2 without 1 would be a dropped fragment.
+int emu_tile_touch(const float* abc6, int X0, int Y0) {
+    float s0x = abc6[4] - abc6[0], s0y = abc6[2] - abc6[0];
+    float s1x = abc6[5] - abc6[1], s1y = abc6[3] - abc6[1];
+    float uz = s0x * s1y - s0y * s1x;
+    if (!(fabsf(uz) > 0.01f)) return 0;
+    float thr = fabsf(uz) * 5.9604644775390625e-08f;
+    int any = 0;
+    for (int y = Y0; y < Y0 + 16 && !any; y++)
+        for (int x = X0; x < X0 + 16; x++) {
+            float ux, uy, s;
+            if (coverage_test(abc6[0], abc6[1], s0x, s0y, s1x, s1y, uz, thr, (float)x, (float)y, ux, uy, s)) {
+                any = 1;
+                break;
+            }
+        }
+    return (tile_may_touch(abc6[0], abc6[1], s0x, s0y, s1x, s1y, uz, thr, (float)X0, (float)Y0) ? 1 : 0) | (any ? 2 : 0);
+}
+
 // graphics_draw_triangle semantics over flat arrays, kernel control flow.
 // tex: u32 B|G<<8|R<<16|A<<24 texels (as hana_texture_upload packs them).
 void emu_draw(int shader, const HanaUniforms* hu, const float* a2v, int ncorners, const uint32_t* dtex, int dw, int dh,

@@ -100,3 +100,40 @@ def test_uniform_prepare_matches_oracle_products(emu, port, hana, horacle):
     assert np.array_equal(got[:16].view(np.uint32), mvp.view(np.uint32))
     assert np.array_equal(got[16:32].view(np.uint32), lmvp.view(np.uint32))
     assert HanaUniforms is not None
+
+
+def test_binning_tile_test_never_drops_a_covered_tile(emu):
+    """tile_may_touch (hana_core.cuh) decides which tile lists a triangle enters. Against exhaustive coverage of every
+    tile a triangle's bounding box meets: it may keep an empty tile, it must never reject one with an inside pixel —
+    random, integer-aligned (edges and vertices exactly on pixels / tile borders), sliver and huge triangles."""
+    rng = np.random.default_rng(7)
+    emu.emu_tile_touch.restype = C.c_int
+    cases = []
+    for _ in range(1500):
+        c = rng.uniform(0, 256, 2)
+        cases.append((c + rng.normal(0, rng.choice([2.0, 12.0, 60.0]), (3, 2))).astype(np.float32))
+    for _ in range(500):  # integer / tile-aligned vertices
+        cases.append(rng.integers(0, 17, (3, 2)).astype(np.float32) * rng.choice([1.0, 8.0, 16.0]))
+    for _ in range(300):  # slivers
+        a = rng.uniform(0, 256, 2)
+        d = rng.normal(0, 80, 2)
+        cases.append(np.stack([a, a + d, a + 0.5 * d + rng.normal(0, 0.05, 2)]).astype(np.float32))
+    for _ in range(100):  # much larger than the window
+        cases.append(rng.uniform(-4000, 4000, (3, 2)).astype(np.float32))
+    kept = rejected = covered = 0
+    for tri in cases:
+        abc = np.ascontiguousarray(tri.reshape(-1))
+        for order in (abc, abc[[0, 1, 4, 5, 2, 3]]):  # both windings: u.z < 0 is the tested path, u.z > 0 always keeps
+            order = np.ascontiguousarray(order)
+            x0, y0 = np.floor(order.reshape(3, 2).min(0) / 16).astype(int) * 16
+            x1, y1 = np.floor(order.reshape(3, 2).max(0) / 16).astype(int) * 16
+            xs = range(max(x0, -64), min(x1, 320) + 1, 16)
+            ys = range(max(y0, -64), min(y1, 320) + 1, 16)
+            for X0 in xs:
+                for Y0 in ys:
+                    r = emu.emu_tile_touch(order.ctypes.data_as(C.c_void_p), int(X0), int(Y0))
+                    assert r != 2, (tri, X0, Y0)
+                    kept += r & 1
+                    rejected += 1 - (r & 1)
+                    covered += r >> 1
+    assert rejected > 0 and covered > 0 and kept >= covered
