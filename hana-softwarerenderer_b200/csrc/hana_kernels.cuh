@@ -563,6 +563,15 @@ __device__ __forceinline__ void clear_slots(const RasterParams& q, RasterSmem<MO
     }
 }
 
+/* atomicAdd whose result is NOT needed yet. nvcc turns an atomicAdd under `if (lane == 0)` into its warp-aggregated
+ * form (vote + one atomic + a shuffle that reads the result at once), which stalls the warp for the whole L2 round trip
+ * and defeats the software pipelining of the work queue below; the PTX form is left alone. */
+__device__ __forceinline__ uint32_t atomic_add_async(uint32_t* addr, uint32_t v) {
+    uint32_t old;
+    asm volatile("atom.global.add.u32 %0, [%1], %2;" : "=r"(old) : "l"(addr), "r"(v) : "memory");
+    return old;
+}
+
 __device__ __forceinline__ uint4 fetch_work(const PassParams& p, uint32_t idx, uint32_t n_work) {
     if (idx < n_work) return __ldg(p.work + idx);
     return make_uint4(WORK_INVALID, 0u, 0u, 0u);
@@ -691,8 +700,8 @@ __global__ void __launch_bounds__(RW_THREADS, ShaderAttrs<SHADER>::LIT ? HANA_OC
         uint32_t i_nn = 0, clr_base = 0;
         if (lane == 0) {
             e_nxt = fetch_work(p, i_next, n_work);
-            i_nn = atomicAdd(&p.counters->work_cursor, 1u);
-            if (MODE != MODE_RMW && !clear_done) clr_base = atomicAdd(&p.counters->clear_cursor, 32u);
+            i_nn = atomic_add_async(&p.counters->work_cursor, 1u);
+            if (MODE != MODE_RMW && !clear_done) clr_base = atomic_add_async(&p.counters->clear_cursor, 32u);
         }
 
         /* -- one non-empty tile -- */
