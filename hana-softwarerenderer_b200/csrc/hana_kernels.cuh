@@ -485,13 +485,6 @@ constexpr int RW_WARPS = 4;
 #ifndef HANA_OCC_OTHER
 #define HANA_OCC_OTHER 7
 #endif
-#ifndef HANA_SHADE_UNROLL
-#define HANA_SHADE_UNROLL 1 /* sub-blocks shaded per iteration of the shading loop */
-#endif
-constexpr int SHADE_UNROLL = HANA_SHADE_UNROLL;
-#ifndef HANA_PREFETCH
-#define HANA_PREFETCH 0
-#endif
 constexpr int RW_THREADS = RW_WARPS * 32;
 constexpr int RW_CHUNK = 32;
 constexpr int RW_REC_Q = 5; /* float4 per staged record */
@@ -787,17 +780,6 @@ __global__ void __launch_bounds__(RW_THREADS, ShaderAttrs<SHADER>::LIT ? HANA_OC
                 }
             }
             __syncwarp();
-#if HANA_PREFETCH
-            if (c0 == 0) { /* the next tile's entry (requested before this tile's records) has arrived by now: pull its
-                              first records towards the SM while this tile is processed */
-                const uint32_t nx_item = __shfl_sync(FULL, e_nxt.x, 0), nx_cnt = __shfl_sync(FULL, e_nxt.y, 0);
-                const uint32_t nx_off = __shfl_sync(FULL, e_nxt.z, 0);
-                if (nx_item != WORK_INVALID && lane < min(nx_cnt, (uint32_t)RW_CHUNK)) {
-                    const float4* nx = p.tile_recs + ((size_t)nx_off + lane) * 4;
-                    asm volatile("prefetch.global.L1 [%0];" ::"l"(nx));
-                }
-            }
-#endif
             for (int j = 0; j < n; j++) {
                 const float4 r0 = wt.tri[j * RW_REC_Q + 0]; /* ax, ay, s0x, s0y */
                 const float4 r1 = wt.tri[j * RW_REC_Q + 1]; /* s1x, s1y, uz, thr */
@@ -942,7 +924,7 @@ __global__ void __launch_bounds__(RW_THREADS, ShaderAttrs<SHADER>::LIT ? HANA_OC
         }
         DevShadow sh = q.shadow;
         if (sh.base) sh.base += (size_t)f * q.shadow_frame_stride;
-#pragma unroll SHADE_UNROLL
+#pragma unroll 1
         for (int sb = 0; sb < 8; sb++) {
             const int pix = pix0 + (sb >> 1) * 64 + (sb & 1) * 8;
             const int px = ipx0 + (sb & 1) * 8, py = ipy0 + (sb >> 1) * 4;
