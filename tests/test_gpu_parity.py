@@ -4,10 +4,13 @@ bit-exact to the real reference by tests/test_oracle_vs_reference.py) on the sam
 Bars (BASELINE.json): coverage / primitive-ID bit-exact except <= 0.01 % of pixels, |depth diff| <= 1e-6,
 |colour diff| <= 1/255 per channel. The implementation is written to be bit-exact in coverage, prim-ID and
 depth, so those are asserted at ZERO mismatches; colour may differ by one level where powf rounds differently."""
+import os
+import sys
+
 import numpy as np
 import pytest
 
-from conftest import cleared, compare_frames
+from conftest import ROOT, cleared, compare_frames
 
 pytestmark = pytest.mark.gpu
 
@@ -267,4 +270,42 @@ def test_equal_depths_later_submission_wins(hana, horacle, port, ctx, blob, copi
     assert np.array_equal(sdep2.view(np.uint32), dep.view(np.uint32))
     assert np.abs(scol2[..., :3].astype(int) - col[..., :3].astype(int)).max() <= 1
     for o in (sw, frame, shadow, model, dtex, ntex):
+        o.close()
+
+
+@pytest.mark.parametrize("shader", ["TEXTURE", "BLINN"])
+def test_positive_uz_slivers(hana, horacle, port, ctx, blob, shader):
+    """Triangles the reference keeps although their screen-space u.z rounds positive (tests/golden/make_slivers.py): the
+    rasteriser stages them with B and C exchanged and exchanges the two quotients back. 1061 such slivers, each
+    covering a pixel in the reference, drawn over an ordinary mesh: primitive ids, depth bits and colours must be the
+    reference's (per-vertex depth and uv differ, so exchanged weights would show in both)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    import make_slivers as ms
+    W, Hh = ms.W, ms.H
+    tris = np.load(os.path.join(ROOT, "tests", "golden", "slivers_posuz.npy"))
+    a2v = np.concatenate([blob.a2v * np.array([0.5, 0.5, 0.5, 1, 1, 1, 1, 1], np.float32), ms.sliver_a2v(tris)])
+    u = ms.identity_uniforms(hana, W, Hh)
+    hu = horacle.HanaUniforms.from_bytes(u.to_bytes())
+    sid, hsid = getattr(hana, shader), getattr(horacle, shader)
+    col, dep = cleared(W, Hh)
+    pid, _ = port.draw(hsid, hu, a2v, W, Hh, col, dep, diffuse=blob.diffuse, normal=blob.normal, want_primid=True)
+    first_sliver = (blob.a2v.shape[0] // 3) * 8
+    assert int((pid[pid != 0xFFFFFFFF] >= first_sliver).sum()) > 500  # the slivers are visible in the reference frame
+    model = ctx.model(a2v)
+    dtex, ntex = ctx.texture(blob.diffuse), ctx.texture(blob.normal)
+    rb = ctx.renderbuffer(W, Hh)
+    c0, d0 = cleared(W, Hh)
+    rb.upload(c0, d0)
+    gpid = ctx.draw(rb, model, sid, u, dtex, ntex, None, want_primid=True)
+    gcol, gdep = rb.download()
+    assert np.array_equal(gpid, pid)
+    assert np.array_equal(gdep.view(np.uint32), dep.view(np.uint32))
+    assert np.abs(gcol[..., :3].astype(int) - col[..., :3].astype(int)).max() <= 1
+    # the sweep path (CLEAR_FOLD + TMA) as well
+    sw = ctx.sweep(W, Hh, 1)
+    sw.render(model, sid, [u], dtex, ntex)
+    scol, sdep = sw.download(0)
+    assert np.array_equal(sdep.view(np.uint32), dep.view(np.uint32))
+    assert np.abs(scol[..., :3].astype(int) - col[..., :3].astype(int)).max() <= 1
+    for o in (sw, rb, model, dtex, ntex):
         o.close()
