@@ -212,6 +212,8 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
     torch.cuda.set_device(local)
     if world > 1:
+        # NCCL's own log lines (e.g. its version banner under NCCL_DEBUG=VERSION) go to stderr: stdout carries ONE JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     F = args.frames
     ctx = hana.Context(local)
