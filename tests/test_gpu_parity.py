@@ -309,3 +309,41 @@ def test_positive_uz_slivers(hana, horacle, port, ctx, blob, shader):
     assert np.abs(scol[..., :3].astype(int) - col[..., :3].astype(int)).max() <= 1
     for o in (sw, rb, model, dtex, ntex):
         o.close()
+
+
+@pytest.mark.parametrize("shader", ["BLINN", "NORMALMAP", "TOON", "TEXTURE_LIGHT"])
+def test_random_soup_crossing_every_clip_plane(hana, horacle, port, ctx, blob, shader):
+    """3 000 random triangles in a box several times the frustum: faces behind the camera (W and near planes), beyond
+    the far plane, across all four side planes, slivers, large and tiny ones, random normals and out-of-range uvs
+    (TGAImage::get returns zeros, tgaimage.cpp:249-251); shadowed two-pass frame against the oracle."""
+    rng = np.random.RandomState(17)
+    n = 3000
+    centre = rng.uniform(-2.5, 2.5, (n, 1, 3))
+    centre[:, :, 2] = rng.uniform(-6.0, 3.0, (n, 1))            # the camera sits at z = 2 looking down -z
+    size = rng.choice([0.02, 0.3, 1.5, 6.0], (n, 1, 1), p=[0.3, 0.4, 0.25, 0.05])
+    pos = centre + rng.normal(0, 1, (n, 3, 3)) * size
+    pos[:8, :, 2] -= rng.uniform(9000, 30000, (8, 3))            # across the far plane (far = 10000)
+    nrm = rng.normal(0, 1, (n, 3, 3))
+    uv = rng.uniform(-0.2, 1.2, (n, 3, 2))
+    a2v = np.concatenate([pos, nrm, uv], axis=2).reshape(-1, 8).astype(np.float32)
+    sc = hana.Scene("soup", a2v, blob.diffuse, blob.normal)
+    W, Hh = 400, 304
+    u = hana.default_uniforms(W, Hh, True)
+    hu = horacle.HanaUniforms.from_bytes(u.to_bytes())
+    col, dep, pid, _, _ = oracle_two_pass(port, horacle, getattr(horacle, shader), hu, sc, W, Hh)
+    assert (pid != 0xFFFFFFFF).mean() > 0.5
+    model, dtex, ntex = sc.upload(ctx)
+    frame, shadow = ctx.renderbuffer(W, Hh), ctx.renderbuffer(W, Hh)
+    for rb in (frame, shadow):
+        rb.clear_color(0, 0, 0, 1)
+        rb.clear_depth(FLT_MAX)
+    ctx.draw_model(frame, shadow, model, getattr(hana, shader), u, dtex, ntex)
+    gcol, gdep = frame.download()
+    check(compare_frames(gcol, gdep, col, dep), W * Hh)
+    gpid = None
+    sw = ctx.sweep(W, Hh, 2)
+    sw.render(model, getattr(hana, shader), [u, u], dtex, ntex)
+    scol, sdep = sw.download(1)
+    check(compare_frames(scol, sdep, col, dep), W * Hh)
+    for o in (sw, frame, shadow, model, dtex, ntex):
+        o.close()
