@@ -153,9 +153,13 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
+            t0 = time.time()
+            while not self.rows and time.time() - t0 < 5.0:  # the sampler is up before the timed region starts
+                time.sleep(0.01)
+            self.first = len(self.rows)
         except OSError:
             self.proc = None
 
@@ -166,7 +170,7 @@ class ClockSampler:
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.02)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
@@ -174,7 +178,8 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], None, set()
         names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
-        for r in self.rows:
+        rows = self.rows[max(getattr(self, "first", 1) - 1, 0):]  # samples from the timed region on (plus the one just before it)
+        for r in rows:
             try:
                 sm.append(float(r[0]))
                 mx = float(r[1])
@@ -190,7 +195,7 @@ class ClockSampler:
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="hana")
     ap.add_argument("--frames", type=int, default=FRAMES_PER_STEP)
