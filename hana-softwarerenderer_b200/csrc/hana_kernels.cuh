@@ -593,7 +593,7 @@ __device__ __forceinline__ bool shade_fragment_t(const FragUniforms& fu, const f
     bool* pb = FAST ? &bad : nullptr;
     if (ShaderAttrs<SHADER>::LIT) {
         const LitAttrs la = interp_lit_packed(ap, w0, w1, w2, pb);
-        fragment_lit_packed<SHADER>(fu, la, diffuse, normal, sh, rgb, pb);
+        fragment_lit_packed<SHADER>(fu, la, diffuse, normal, sh, ap, rgb, pb);
         return bad;
     }
     const float4 rw = __ldg(ap);
@@ -613,26 +613,27 @@ __device__ __forceinline__ bool shade_fragment_t(const FragUniforms& fu, const f
     fragment_shader<SHADER>(fu, attr, diffuse, normal, sh, rgb, pb);
     return bad;
 }
+/* The rare re-evaluation with the full sqrt / reciprocal functions. Returns the colour bytes (by value: an rgb[] passed by
+ * address into a non-inlined call would live in local memory in the caller's hot loop). */
 template <int SHADER>
-__device__ __noinline__ void shade_fragment_exact(const FragUniforms* fu, const float4* ap, float w0, float w1, float w2,
-                                                  const DevTexture* diffuse, const DevTexture* normal, const DevShadow* sh,
-                                                  float* rgb) {
+__device__ __noinline__ uint32_t shade_fragment_exact(const FragUniforms* fu, const float4* ap, float w0, float w1, float w2,
+                                                      const DevTexture* diffuse, const DevTexture* normal, const DevShadow* sh) {
     float c[3];
     shade_fragment_t<SHADER, false>(*fu, ap, w0, w1, w2, *diffuse, *normal, *sh, c);
-    rgb[0] = c[0];
-    rgb[1] = c[1];
-    rgb[2] = c[2];
+    return colour_bytes(c);
 }
+/* graphics.cpp:362-373 for one fragment: the R,G,B bytes set_color stores (renderbuffer.cpp:38-44) */
 template <int SHADER>
-__device__ __forceinline__ void shade_fragment(const FragUniforms& fu, const float4* ap, float w0, float w1, float w2,
-                                               const DevTexture& diffuse, const DevTexture& normal, const DevShadow& sh,
-                                               float rgb[3]) {
+__device__ __forceinline__ uint32_t shade_fragment(const FragUniforms& fu, const float4* ap, float w0, float w1, float w2,
+                                                   const DevTexture& diffuse, const DevTexture& normal, const DevShadow& sh) {
+    float rgb[3];
     if (ShaderAttrs<SHADER>::LIT) { /* ten sqrt/reciprocal sites: worth the shared range check */
         if (shade_fragment_t<SHADER, true>(fu, ap, w0, w1, w2, diffuse, normal, sh, rgb)) /* an operand left the fast paths' range */
-            shade_fragment_exact<SHADER>(&fu, ap, w0, w1, w2, &diffuse, &normal, &sh, rgb);
+            return shade_fragment_exact<SHADER>(&fu, ap, w0, w1, w2, &diffuse, &normal, &sh);
     } else {
         shade_fragment_t<SHADER, false>(fu, ap, w0, w1, w2, diffuse, normal, sh, rgb);
     }
+    return colour_bytes(rgb);
 }
 
 template <int SHADER, int MODE>
@@ -704,6 +705,7 @@ __global__ void __launch_bounds__(RW_THREADS, ShaderAttrs<SHADER>::LIT ? HANA_OC
         const uint32_t cnt = cur.y;
         const float4* list = p.tile_recs + (size_t)cur.z * 4;
         const float4* frame_rec = p.tri_rec + (size_t)f * p.tri_cap * 4; /* the frame's records by slot: tie-breaks, primitive ids */
+        const float4* frame_attr = p.tri_attr + (size_t)f * p.tri_cap * NQ; /* ... and their attribute blocks */
         if (ShaderAttrs<SHADER>::READS_UNIFORMS && lane < sizeof(FragUniforms) / 16) /* read again only after the __syncwarp()s of the record loop */
             reinterpret_cast<float4*>(&wt.fu)[lane] = __ldg(reinterpret_cast<const float4*>(&p.uniforms[f].frag) + lane);
         const float fpx0 = (float)(X0 + lx), fpx1 = (float)(X0 + 8 + lx);
@@ -937,10 +939,8 @@ __global__ void __launch_bounds__(RW_THREADS, ShaderAttrs<SHADER>::LIT ? HANA_OC
             }
             if (slot != ORD_NONE) {
                 const float w0 = pw0[pix], w1 = wt.pw1[pix], w2 = wt.pw2[pix];
-                const float4* ap = p.tri_attr + ((size_t)f * p.tri_cap + slot) * NQ;
-                float rgb[3];
-                shade_fragment<SHADER>(wt.fu, ap, w0, w1, w2, q.diffuse, q.normal, sh, rgb);
-                col = (col & 0xFF000000u) | colour_bytes(rgb); /* alpha is never written: renderbuffer.cpp:38-44 */
+                const float4* ap = frame_attr + (size_t)slot * NQ;
+                col = (col & 0xFF000000u) | shade_fragment<SHADER>(wt.fu, ap, w0, w1, w2, q.diffuse, q.normal, sh); /* alpha is never written: renderbuffer.cpp:38-44 */
                 if (q.primid && f == 0) q.primid[(size_t)py * p.W + px] = __float_as_uint(__ldg(frame_rec + (size_t)slot * 4 + 2).w);
             }
             if (q.pixels_covered) covered_acc += __popc(__ballot_sync(FULL, slot != ORD_NONE));
