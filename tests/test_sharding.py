@@ -191,6 +191,34 @@ def test_split_frame_bands_on_one_gpu(hana, ctx):
 
 
 @pytest.mark.gpu
+def test_split_frame_api_errors_and_band_isolation(hana, ctx):
+    """Argument checks of the band API, and that a band render leaves every tile row outside the band untouched."""
+    W, H = 128, 96
+    scene = hana.synthetic_scene("blob", tex=32)
+    model, dtex, ntex = scene.upload(ctx)
+    u = hana.default_uniforms(W, H, False)
+    sw = ctx.sweep(W, H, 1)
+    with pytest.raises(hana.HanaError):
+        sw.set_bands(shadow=(-1, 2))
+    with pytest.raises(hana.HanaError):
+        sw.render_pass(7, model, hana.BLINN, [u], dtex, ntex)
+    sw.render(model, hana.GROUND, [u], dtex, ntex, clear_rgba=(9, 9, 9, 1))      # whole frame, grey background
+    c0, d0 = sw.download(0)
+    sw.set_bands(main=(2, 2))                                                      # tile rows 2..3 = pixel rows 32..63
+    sw.render_pass(hana.PASS_MAIN, model, hana.BLINN, [u], dtex, ntex, clear_rgba=(0, 0, 0, 1))
+    c1, d1 = sw.download(0)
+    assert np.array_equal(c1[:32], c0[:32]) and np.array_equal(c1[64:], c0[64:])   # outside the band: the first render
+    assert np.array_equal(d1[:32], d0[:32]) and np.array_equal(d1[64:], d0[64:])
+    assert not np.array_equal(c1[32:64], c0[32:64])                                # inside: re-rendered with Blinn on black
+    sw.set_bands()
+    sw.render(model, hana.BLINN, [u], dtex, ntex)
+    c2, d2 = sw.download(0)
+    assert np.array_equal(c1[32:64, :, :3], c2[32:64, :, :3]) and np.array_equal(d1[32:64], d2[32:64])
+    for o in (sw, model, dtex, ntex):
+        o.close()
+
+
+@pytest.mark.gpu
 def test_split_frame_two_gpus_match_one_gpu(hana, tmp_path):
     if hana.device_count() < 2:
         pytest.skip("needs 2 GPUs")
