@@ -135,6 +135,8 @@ def load():
         "hana_sweep_set_bands": [vp, i, i, i, i],
         "hana_sweep_render_pass": [vp, i, vp, i, vp, i, vp, vp, vp, f],
         "hana_sweep_shadow_ptrs": [vp, C.POINTER(vp), C.POINTER(i), C.POINTER(C.c_size_t)],
+        "hana_sweep_render_pass_async": [vp, i, vp, i, vp, i, vp, vp, vp, f],
+        "hana_sweep_passes_ok": [vp, C.POINTER(i)],
         "hana_tga_write": [C.c_char_p, vp, i, i, i, i],
         "hana_obj_load": [C.c_char_p, i, C.POINTER(vp), C.POINTER(i)],
         "hana_tga_load": [C.c_char_p, i, C.POINTER(vp), C.POINTER(i), C.POINTER(i), C.POINTER(i)],
@@ -411,6 +413,20 @@ class Sweep:
         clr = (C.c_uint8 * 4)(*clear_rgba)
         _ck(self.ctx.L.hana_sweep_render_pass(self.h, int(which), model.h, shader, arr, len(arr), _h(diffuse), _h(normal), clr,
                                               float(clear_depth)))
+
+    def render_pass_async(self, which, model, shader, uniforms, diffuse=None, normal=None, clear_rgba=(0, 0, 0, 1),
+                          clear_depth=FLT_MAX):
+        """render_pass queued without any host synchronisation; passes_ok() afterwards."""
+        arr = uniforms if isinstance(uniforms, C.Array) else self.pack_uniforms(uniforms)
+        clr = (C.c_uint8 * 4)(*clear_rgba)
+        _ck(self.ctx.L.hana_sweep_render_pass_async(self.h, int(which), model.h, shader, arr, len(arr), _h(diffuse), _h(normal),
+                                                    clr, float(clear_depth)))
+
+    def passes_ok(self):
+        """Waits for the queued passes; False if scratch ran out (it has been grown: queue the frame again)."""
+        ok = C.c_int()
+        _ck(self.ctx.L.hana_sweep_passes_ok(self.h, C.byref(ok)))
+        return bool(ok.value)
 
     def device_planes(self):
         """(colour ptr, depth ptr, frame stride in pixels) of the frame ring; synchronises."""

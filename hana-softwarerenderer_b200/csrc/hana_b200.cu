@@ -1122,7 +1122,7 @@ static int sweep_render_passes(hana_sweep* s, const hana_model* model, int shade
         d.pool_cap_used = &s->pending.pool_cap;
         d.band_first = s->band[0][0];
         d.band_count = s->band[0][1];
-        if (lazy) { /* fork: the main pass is binned on the side stream while this one is binned here */
+        if (lazy && passes == SWEEP_PASS_BOTH) { /* fork: the main pass is binned on the side stream while this one is binned here */
             CU_TRY(cudaEventRecord(ctx->ev_fork, ctx->stream));
             CU_TRY(cudaStreamWaitEvent(ctx->side_stream, ctx->ev_fork, 0));
             d.phase = 1;
@@ -1173,7 +1173,7 @@ static int sweep_render_passes(hana_sweep* s, const hana_model* model, int shade
     uint32_t tc = 0, pc = 0;
     d.tri_cap_used = &tc;
     d.pool_cap_used = &pc;
-    if (lazy && enable_shadow) {
+    if (lazy && enable_shadow && passes == SWEEP_PASS_BOTH) {
         d.phase = 1;
         d.scratch = 1;
         d.stream = ctx->side_stream;
@@ -1326,6 +1326,57 @@ extern "C" int hana_sweep_render_pass(hana_sweep* s, int pass, const hana_model*
     /* with read-backs (not lazy): a split frame is one large frame, not a stream of small ones */
     return sweep_render_passes(s, model, shader_id, uniforms[0].enable_shadow != 0, n_frames, diffuse, normal, clear_rgba, clear_depth,
                                false, pass == HANA_PASS_SHADOW ? SWEEP_PASS_SHADOW : SWEEP_PASS_MAIN);
+}
+
+/* The same pass queued without any read-back (scratch capacities are the context's current ones), so that a caller
+ * whose collectives run on the context's stream (hana_ctx_set_stream) never synchronises the host inside a frame. */
+extern "C" int hana_sweep_render_pass_async(hana_sweep* s, int pass, const hana_model* model, int shader_id,
+                                            const HanaUniforms* uniforms, int n_frames, const hana_texture* diffuse,
+                                            const hana_texture* normal, const uint8_t clear_rgba[4], float clear_depth) {
+    if (!s) return fail(HANA_E_INVALID, "sweep is NULL");
+    if (pass != HANA_PASS_SHADOW && pass != HANA_PASS_MAIN) return fail(HANA_E_INVALID, "pass is HANA_PASS_SHADOW or HANA_PASS_MAIN");
+    HANA_TRY(check_draw_args(s->ctx, model, uniforms, pass == HANA_PASS_SHADOW ? HANA_SHADER_SHADOW : shader_id));
+    if (!clear_rgba) return fail(HANA_E_INVALID, "clear_rgba is NULL");
+    if (n_frames < 1 || n_frames > s->max_frames) return fail(HANA_E_INVALID, "n_frames outside 1..max_frames");
+    hana_ctx* ctx = s->ctx;
+    HANA_TRY(use_device(ctx));
+    const bool shadowed = uniforms[0].enable_shadow != 0;
+    const bool first = pass == HANA_PASS_SHADOW || !shadowed; /* first pass of the frame: new uniforms, needs start from zero */
+    if (first) {
+        HANA_TRY(sweep_verify(s));
+        s->pending.active = false;
+        if (s->copy_in_flight) {
+            CU_TRY(cudaStreamWaitEvent(ctx->stream, s->ev_copy, 0));
+            s->copy_in_flight = false;
+        }
+        HANA_TRY(upload_uniforms(ctx, uniforms, n_frames, s->u_raw, s->u_dev));
+        CU_TRY(cudaMemsetAsync(s->overflow, 0, sizeof(OverflowRecord), ctx->stream));
+        s->pending.tri_cap = s->pending.pool_cap = 0xFFFFFFFFu;
+    }
+    if (pass == HANA_PASS_SHADOW && !shadowed) return HANA_OK; /* scene.h:73: no shadow pass */
+    HANA_TRY(sweep_render_passes(s, model, shader_id, shadowed, n_frames, diffuse, normal, clear_rgba, clear_depth, true,
+                                 pass == HANA_PASS_SHADOW ? SWEEP_PASS_SHADOW : SWEEP_PASS_MAIN));
+    s->pending.active = false; /* nothing to re-render behind the caller's back: hana_sweep_passes_ok reports instead */
+    return HANA_OK;
+}
+
+/* Waits for the passes queued by hana_sweep_render_pass_async. *ok = 0 if one of them ran out of triangle or tile-list
+ * scratch (fragments were dropped): the scratch has been grown, queue the frame again. */
+extern "C" int hana_sweep_passes_ok(hana_sweep* s, int* ok) {
+    if (!s || !ok) return fail(HANA_E_INVALID, "NULL argument");
+    hana_ctx* ctx = s->ctx;
+    HANA_TRY(use_device(ctx));
+    CU_TRY(cudaMemcpyAsync(&s->pin->need, s->overflow, sizeof(OverflowRecord), cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(cudaStreamSynchronize(ctx->stream));
+    const OverflowRecord need = s->pin->need;
+    *ok = (need.tri_needed <= s->pending.tri_cap && need.pool_needed <= s->pending.pool_cap) ? 1 : 0;
+    if (!*ok) {
+        ctx->tri_cap_hint = std::max(ctx->tri_cap_hint, need.tri_needed + need.tri_needed / 8 + 64);
+        for (Scratch* sp : {&ctx->sc, &ctx->sc2})
+            if ((size_t)need.pool_needed > sp->pool_cap / 4 && (sp == &ctx->sc || sp->tile_recs))
+                HANA_TRY(grow(&sp->tile_recs, &sp->pool_cap, ((size_t)need.pool_needed + need.pool_needed / 4) * 4, ctx));
+    }
+    return HANA_OK;
 }
 
 extern "C" int hana_sweep_shadow_ptrs(hana_sweep* s, void** r8_dev, int* pitch_bytes, size_t* frame_stride_bytes) {

@@ -141,6 +141,67 @@ def render_split_frame(ctx, hana, sweep, scene_objs, shader, uniforms, rank, wor
     return moved
 
 
+def render_split_frame_async(ctx, hana, sweep, scene_objs, shader, uniforms, rank, world, device, exchange_shadow=True,
+                             max_attempts=4):
+    """render_split_frame without a host synchronisation inside the frame: the context launches on torch's current
+    stream, so pass 1 -> all-gather of the shadow bands -> pass 2 -> all-gather of the colour / depth bands are ordered
+    by the stream (NCCL collectives wait for, and are waited for by, the current stream). Scratch needs cannot be read
+    back in between, so the ranks agree afterwards (one all-reduce of a flag) whether any of them ran out; if so all of
+    them queue the frame again with the grown scratch. Returns the number of attempts."""
+    import torch
+    import torch.distributed as dist
+
+    model, dtex, ntex = scene_objs
+    W, H = sweep.width, sweep.height
+    bands = tile_row_bands(H, world)
+    rows = [band_pixel_rows(b, H) for b in bands]
+    mine = bands[rank]
+    past = ((H + TILE - 1) // TILE, 1)
+    mine = past if mine[1] == 0 else mine
+    shadowed = bool(uniforms.enable_shadow)
+    sptr, pitch, sstride = sweep.shadow_plane()   # pointers are stable: fetch them before anything is queued
+    cptr, dptr, _ = sweep.device_planes()
+    splane = device_plane_tensor(sptr, sstride, device)
+    planes = [device_plane_tensor(p, W * H * 4, device) for p in (cptr, dptr)]
+    on_gpu = str(device).startswith("cuda")
+    import contextlib
+    scope = contextlib.nullcontext()
+    if on_gpu:
+        # a stream of torch's own (its default stream is handle 0, which the C ABI reads as "the context's stream")
+        global _SPLIT_STREAM
+        if _SPLIT_STREAM is None:
+            _SPLIT_STREAM = torch.cuda.Stream()
+        _SPLIT_STREAM.wait_stream(torch.cuda.current_stream())
+        ctx.sync()
+        ctx.set_stream(_SPLIT_STREAM.cuda_stream)
+        scope = torch.cuda.stream(_SPLIT_STREAM)
+    try:
+      with scope:
+        sweep.set_bands(shadow=mine if exchange_shadow else (0, 0), main=mine)
+        for attempt in range(1, max_attempts + 1):
+            if shadowed:
+                sweep.render_pass_async(hana.PASS_SHADOW, model, shader, [uniforms], dtex, ntex)
+                if exchange_shadow:
+                    exchange_bands(splane, pitch, rows, rank, world)
+            sweep.render_pass_async(hana.PASS_MAIN, model, shader, [uniforms], dtex, ntex)
+            for pl in planes:
+                exchange_bands(pl, W * 4, rows, rank, world)
+            ok = torch.tensor([int(sweep.passes_ok())], dtype=torch.int32, device=device)
+            if world > 1:
+                dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if int(ok.item()):
+                return attempt
+        raise hana.HanaError(-5, "split frame still short of scratch after %d attempts" % max_attempts)
+    finally:
+        sweep.set_bands()
+        if on_gpu:
+            _SPLIT_STREAM.synchronize()
+            ctx.set_stream(None)
+
+
+_SPLIT_STREAM = None
+
+
 def _sync(device):
     import torch
 

@@ -269,6 +269,15 @@ HANA_API int hana_sweep_render_pass(hana_sweep* s, int pass, const hana_model* m
                            const HanaUniforms* uniforms, int n_frames, const hana_texture* diffuse,
                            const hana_texture* normal, const uint8_t clear_rgba[4], float clear_depth);
 HANA_API int hana_sweep_shadow_ptrs(hana_sweep* s, void** r8_dev, int* pitch_bytes, size_t* frame_stride_bytes);
+/* hana_sweep_render_pass without host synchronisation: the pass is queued on the context's stream with the scratch
+ * capacities the context has (hana_sweep_render_pass reads the needs back and retries by itself). With the context on
+ * the caller's stream (hana_ctx_set_stream) the exchanges between the passes are ordered by the stream alone.
+ * hana_sweep_passes_ok waits for the queued passes and reports whether both had room (*ok = 1); if not, the scratch has
+ * been grown and the frame must be queued again — on every rank of a split frame, or none. */
+HANA_API int hana_sweep_render_pass_async(hana_sweep* s, int pass, const hana_model* model, int shader_id,
+                                 const HanaUniforms* uniforms, int n_frames, const hana_texture* diffuse,
+                                 const hana_texture* normal, const uint8_t clear_rgba[4], float clear_depth);
+HANA_API int hana_sweep_passes_ok(hana_sweep* s, int* ok);
 
 /* --- present / output ------------------------------------ */
 /* Replaces window_draw_buffer's conversion loop (win32.cpp:348-370): frames [first, first+count) of the last batch

@@ -125,6 +125,10 @@ else:
             hana.sharding.render_split_frame(ctx, hana, sweep, objs, hana.NORMALMAP, u, rank, world, "cuda", exchange_shadow=exchange)
             sums.append(int(sweep.checksums(1)[0]))
             sweep.close()
+        sweep = ctx.sweep(w, h, 1)   # the stream-ordered form: no host synchronisation inside the frame
+        hana.sharding.render_split_frame_async(ctx, hana, sweep, objs, hana.NORMALMAP, u, rank, world, "cuda")
+        sums.append(int(sweep.checksums(1)[0]))
+        sweep.close()
     res = np.array(sums, np.uint64)
     t = torch.from_numpy(res.view(np.int64).copy()).cuda()
     out = [torch.zeros_like(t) for _ in range(world)]
@@ -224,6 +228,6 @@ def test_split_frame_two_gpus_match_one_gpu(hana, tmp_path):
         pytest.skip("needs 2 GPUs")
     two = run_split_workers("gpu", 2, tmp_path / "two.npy", tmp_path)
     one = run_split_workers("gpu", 1, tmp_path / "one.npy", tmp_path)
-    assert two.shape == (8,) and one.shape == (4,)
-    assert one[0] == one[1] and one[2] == one[3] and one[0] != one[2]
-    assert np.array_equal(two[:4], one) and np.array_equal(two[4:], one)  # both ranks hold both complete frames
+    assert two.shape == (12,) and one.shape == (6,)
+    assert one[0] == one[1] == one[2] and one[3] == one[4] == one[5] and one[0] != one[3]
+    assert np.array_equal(two[:6], one) and np.array_equal(two[6:], one)  # both ranks hold both complete frames

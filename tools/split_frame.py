@@ -66,6 +66,25 @@ def main():
         out["exchange_shadow_bands" if exchange else "redundant_shadow_pass"] = {
             "ms_per_frame": float(t.item()), "checksum_equals_unsplit_on_every_rank": bool(ok.item()), **moved}
         sw.close()
+    # stream-ordered form: passes and NCCL exchanges on one stream, one host synchronisation per frame
+    sw = ctx.sweep(W, H, 1)
+    attempts = hana.sharding.render_split_frame_async(ctx, hana, sw, objs, hana.NORMALMAP, u, rank, world, "cuda")
+    got = int(sw.checksums(1)[0])
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        hana.sharding.render_split_frame_async(ctx, hana, sw, objs, hana.NORMALMAP, u, rank, world, "cuda")
+    torch.cuda.synchronize()
+    t = torch.tensor([(time.perf_counter() - t0) * 1e3 / reps], dtype=torch.float64, device="cuda")
+    ok = torch.tensor([int(got == want)], dtype=torch.int64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+    out["stream_ordered"] = {"ms_per_frame": float(t.item()), "checksum_equals_unsplit_on_every_rank": bool(ok.item()),
+                             "first_call_attempts": attempts}
+    sw.close()
     if rank == 0:
         print(json.dumps({"config": "configs[4] split by tile rows", "width": W, "height": H, "n_gpus": world, "faces": sc.nfaces,
                           "ms_per_frame_unsplit_1gpu": ms_unsplit, **out}))
