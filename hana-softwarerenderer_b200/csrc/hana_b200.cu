@@ -770,6 +770,16 @@ static int run_pass(hana_ctx* ctx, const PassDesc& d) {
             ctx->launches++;
             CU_TRY(cudaGetLastError());
         }
+        /* (triangle, tile) pairs: gridDim.z warps share the rounds of 32 triangles when triangles cover many tiles each */
+        const unsigned pair_z = (unsigned)std::min<size_t>(16, std::max<size_t>(1, n_tiles / (size_t)std::max(nfaces, 1) / 2));
+        if (nfaces > 0) {
+            dim3 grid((tri_cap + 255) / 256, d.n_frames, pair_z);
+            prof_begin(ctx, PROF_SETUP, &ea, &eb, st);
+            pairs_kernel<false><<<grid, 256, 0, st>>>(p);
+            prof_end(ctx, PROF_SETUP, ea, eb, st);
+            ctx->launches++;
+            CU_TRY(cudaGetLastError());
+        }
         prof_begin(ctx, PROF_SCAN, &ea, &eb, st);
         scan_kernel<<<dim3((unsigned)((n_tiles + SCAN_CHUNK - 1) / SCAN_CHUNK), (unsigned)d.n_frames), SCAN_THREADS, 0, st>>>(p);
         prof_end(ctx, PROF_SCAN, ea, eb, st);
@@ -820,10 +830,11 @@ static int run_pass(hana_ctx* ctx, const PassDesc& d) {
 
     cudaEvent_t ea, eb;
     if (cnt.pool_used > 0 && d.phase != 2) {
-        dim3 grid((std::min(cnt.tri_needed, tri_cap) + 255) / 256, d.n_frames);
+        const unsigned pair_z = (unsigned)std::min<size_t>(16, std::max<size_t>(1, n_tiles / (size_t)std::max(nfaces, 1) / 2));
+        dim3 grid((std::min(cnt.tri_needed, tri_cap) + 255) / 256, d.n_frames, pair_z);
         if (grid.x > 0) {
             prof_begin(ctx, PROF_FILL, &ea, &eb, st);
-            fill_kernel<<<grid, 256, 0, st>>>(p);
+            pairs_kernel<true><<<grid, 256, 0, st>>>(p);
             prof_end(ctx, PROF_FILL, ea, eb, st);
             ctx->launches++;
             CU_TRY(cudaGetLastError());

@@ -3,9 +3,10 @@
  *
  *   begin_kernel   HanaUniforms -> DevUniforms (matrix products hoisted), counters zeroed
  *   setup_kernel   vertex shading + homogeneous clip + cull + triangle setup, warp-scan
- *                  compaction of the surviving triangles, per-tile reference counts
+ *                  compaction of the surviving triangles
+ *   pairs_kernel   <false>: per-tile counts of the triangles that can touch the tile; <true>: see fill
  *   scan_kernel    exclusive scan of the tile counts -> list offsets + non-empty tile queue
- *   fill_kernel    triangle raster records copied into the per-tile lists (no indirection in the rasteriser)
+ *   pairs_kernel<true>  ("fill") triangle raster records copied into the per-tile lists (no indirection in the rasteriser)
  *   raster_kernel  persistent CTAs, one 16x16 tile at a time: coverage + depth resolve in
  *                  registers, shading of the winning fragment, tile flush by TMA store;
  *                  empty tiles are cleared by fire-and-forget TMA stores from a constant tile
@@ -228,15 +229,12 @@ __device__ __forceinline__ void store_triangle(const PassParams& p, int f, uint3
     }
 }
 
-__device__ __forceinline__ void count_tiles(const PassParams& p, int f, const TriRecord& r) {
-    int tx0 = (int)(r.bbx & 0xFFFFu) >> 4, tx1 = (int)(r.bbx >> 16) >> 4;
+/* A triangle whose pixel range lies inside ONE tile (of the pass's band) is counted right here; the others are left to
+ * pairs_kernel<false>, which skips these (dense meshes are almost all single-tile triangles: BASELINE.json configs[3]). */
+__device__ __forceinline__ void count_single_tile(const PassParams& p, int f, const TriRecord& r) {
+    const int tx0 = (int)(r.bbx & 0xFFFFu) >> 4, tx1 = (int)(r.bbx >> 16) >> 4;
     const int ty0 = max((int)(r.bby & 0xFFFFu) >> 4, p.band_y0), ty1 = min((int)(r.bby >> 16) >> 4, p.band_y1 - 1);
-    uint32_t* tc = p.tile_count + (size_t)f * p.tile_pad;
-    const bool single = tx0 == tx1 && ty0 == ty1; /* a range inside one tile: the triangle touches it or covers nothing */
-    for (int ty = ty0; ty <= ty1; ty++)
-        for (int tx = tx0; tx <= tx1; tx++)
-            if (single || tile_may_touch(r.ax, r.ay, r.s0x, r.s0y, r.s1x, r.s1y, r.uz, r.thr, (float)(tx * TILE), (float)(ty * TILE)))
-                atomicAdd(tc + tile_slot(p, ty * p.tiles_x + tx), 1u);
+    if (tx0 == tx1 && ty0 == ty1) atomicAdd(p.tile_count + (size_t)f * p.tile_pad + tile_slot(p, ty0 * p.tiles_x + tx0), 1u);
 }
 
 /* Rare path: the face is not trivially accepted. Sutherland-Hodgman in local
@@ -255,7 +253,7 @@ __device__ __noinline__ void setup_clipped(const PassParams& p, int f, int face,
         uint32_t slot = atomicAdd(p.tri_count + f, 1u);
         if (slot < p.tri_cap) {
             store_triangle<SHADER>(p, f, slot, r, a, b, c);
-            count_tiles(p, f, r);
+            count_single_tile(p, f, r);
         }
     }
 }
@@ -311,7 +309,7 @@ __global__ void __launch_bounds__(SETUP_THREADS) setup_kernel(PassParams p) {
         const uint32_t slot = s_cta_base + s_warp_total[wid] + (uint32_t)(incl - 1);
         if (slot < p.tri_cap) {
             store_triangle<SHADER>(p, f, slot, r, v, v + V2F_N, v + 2 * V2F_N);
-            count_tiles(p, f, r);
+            count_single_tile(p, f, r);
         }
     }
 }
@@ -389,19 +387,24 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_kernel(PassParams p) {
     }
 }
 
-/* ---- fill: raster records into the tile lists ---------------------------------
- * A lane owns one triangle, but the (triangle, tile) pairs of the whole warp are flattened by a
- * shuffle prefix sum and dealt out round-robin, so every list-slot atomic of a round is independent
- * (a triangle covering 100 tiles costs its warp 4 rounds instead of one lane 100 dependent ones). */
-__global__ void __launch_bounds__(256) fill_kernel(PassParams p) {
+/* ---- count / fill: the (triangle, tile) pairs ------------------------------------
+ * pairs_kernel<false> counts, for every 16x16 tile, the triangles that can touch it (tile_may_touch over the tiles of
+ * the triangle's pixel range, clamped to the pass's band); pairs_kernel<true>, after the scan, copies each raster
+ * record into those tiles' lists. Both enumerate the pairs the same way: a lane owns one triangle, but the pairs of the
+ * whole warp are flattened by a shuffle prefix sum and dealt out round-robin, so the atomics of a round are independent
+ * (a triangle covering 100 tiles costs its warp 4 rounds instead of one lane 100 dependent ones); gridDim.z warps share
+ * the rounds of the same 32 triangles, which is what keeps the SMs busy when a few thousand triangles cover hundreds of
+ * tiles each (BASELINE.json configs[4]). */
+template <bool FILL>
+__global__ void __launch_bounds__(256) pairs_kernel(PassParams p) {
     constexpr unsigned FULL = 0xFFFFFFFFu;
     const int f = blockIdx.y;
     const uint32_t i = blockIdx.x * 256u + threadIdx.x;
     const unsigned lane = threadIdx.x & 31u;
     uint32_t n = p.tri_count[f];
     if (n > p.tri_cap) n = p.tri_cap;
-    if ((i & ~31u) >= n) return;                    /* whole warp past the end */
-    if (p.counters->pool_used > p.pool_cap) return; /* host re-runs the pass with a larger pool */
+    if ((i & ~31u) >= n) return;                            /* whole warp past the end */
+    if (FILL && p.counters->pool_used > p.pool_cap) return; /* host re-runs the pass with a larger pool */
     const float4* warp_rec = p.tri_rec + ((size_t)f * p.tri_cap + (i & ~31u)) * 4;
     int tx0 = 0, ty0 = 0, ntx = 1, nt = 0;
     if (i < n) {
@@ -411,6 +414,7 @@ __global__ void __launch_bounds__(256) fill_kernel(PassParams p) {
         ty0 = max((int)(bby & 0xFFFFu) >> 4, p.band_y0);
         ntx = ((int)(bbx >> 16) >> 4) - tx0 + 1;
         nt = ntx * max(min((int)(bby >> 16) >> 4, p.band_y1 - 1) - ty0 + 1, 0);
+        if (!FILL && nt == 1) nt = 0; /* counted by setup_kernel (count_single_tile) */
     }
     int incl = nt;
 #pragma unroll
@@ -420,9 +424,10 @@ __global__ void __launch_bounds__(256) fill_kernel(PassParams p) {
     }
     const int excl = incl - nt;
     const int total = __shfl_sync(FULL, incl, 31);
+    uint32_t* cnt = p.tile_count + (size_t)f * p.tile_pad;
     uint32_t* cur = p.tile_cursor + (size_t)f * p.tile_pad;
     const uint32_t* to = p.tile_offset + (size_t)f * p.n_tiles;
-    for (int base = 0; base < total; base += 32) {
+    for (int base = (int)blockIdx.z * 32; base < total; base += 32 * (int)gridDim.z) {
         const int k = base + (int)lane;
         /* owner of pair k: the last lane whose exclusive prefix is <= k (it has nt > 0 whenever k < total) */
         int j = 0;
@@ -433,20 +438,26 @@ __global__ void __launch_bounds__(256) fill_kernel(PassParams p) {
         }
         const int local = k - __shfl_sync(FULL, excl, j);
         const int jtx0 = __shfl_sync(FULL, tx0, j), jty0 = __shfl_sync(FULL, ty0, j), jntx = __shfl_sync(FULL, ntx, j);
-        const bool single = __shfl_sync(FULL, nt, j) == 1; /* same decision as count_tiles() */
+        const bool single = __shfl_sync(FULL, nt, j) == 1; /* a range inside one tile: the triangle touches it or covers nothing */
         if (k < total) {
             const float4* rec = warp_rec + j * 4;
-            const float4 q0 = __ldg(rec), q1 = __ldg(rec + 1), q2 = __ldg(rec + 2), q3 = __ldg(rec + 3);
+            const float4 q0 = __ldg(rec), q1 = __ldg(rec + 1);
             const int row = local / jntx;
             const int tx = jtx0 + (local - row * jntx), ty = jty0 + row;
             const int t = ty * p.tiles_x + tx;
+            /* the same operands in both instantiations: the count and the fill agree */
             if (single || tile_may_touch(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, (float)(tx * TILE), (float)(ty * TILE))) {
-                const uint32_t s = atomicAdd(cur + tile_slot(p, t), 1u);
-                float4* d = p.tile_recs + ((size_t)__ldg(to + t) + s) * 4;
-                d[0] = q0;
-                d[1] = q1;
-                d[2] = q2;
-                d[3] = q3;
+                if (!FILL) {
+                    atomicAdd(cnt + tile_slot(p, t), 1u);
+                } else {
+                    const float4 q2 = __ldg(rec + 2), q3 = __ldg(rec + 3);
+                    const uint32_t s = atomicAdd(cur + tile_slot(p, t), 1u);
+                    float4* d = p.tile_recs + ((size_t)__ldg(to + t) + s) * 4;
+                    d[0] = q0;
+                    d[1] = q1;
+                    d[2] = q2;
+                    d[3] = q3;
+                }
             }
         }
     }
