@@ -231,10 +231,21 @@ __device__ __forceinline__ void store_triangle(const PassParams& p, int f, uint3
 
 /* A triangle whose pixel range lies inside ONE tile (of the pass's band) is counted right here; the others are left to
  * pairs_kernel<false>, which skips these (dense meshes are almost all single-tile triangles: BASELINE.json configs[3]). */
-__device__ __forceinline__ void count_single_tile(const PassParams& p, int f, const TriRecord& r) {
+/* the counter slot of the single tile a triangle's pixel range lies in, or -1 */
+__device__ __forceinline__ int single_tile_slot(const PassParams& p, const TriRecord& r) {
     const int tx0 = (int)(r.bbx & 0xFFFFu) >> 4, tx1 = (int)(r.bbx >> 16) >> 4;
     const int ty0 = max((int)(r.bby & 0xFFFFu) >> 4, p.band_y0), ty1 = min((int)(r.bby >> 16) >> 4, p.band_y1 - 1);
-    if (tx0 == tx1 && ty0 == ty1) atomicAdd(p.tile_count + (size_t)f * p.tile_pad + tile_slot(p, ty0 * p.tiles_x + tx0), 1u);
+    return (tx0 == tx1 && ty0 == ty1) ? tile_slot(p, ty0 * p.tiles_x + tx0) : -1;
+}
+__device__ __forceinline__ void count_single_tile(const PassParams& p, int f, const TriRecord& r) {
+    const int s = single_tile_slot(p, r);
+    if (s >= 0) atomicAdd(p.tile_count + (size_t)f * p.tile_pad + s, 1u);
+}
+/* Warp-aggregated: the lanes of a warp that count into the same tile (neighbouring faces of a dense mesh) send ONE
+ * atomic. Every lane of the warp calls this (key < 0: nothing to count). */
+__device__ __forceinline__ void count_aggregated(uint32_t* counters, int key) {
+    const unsigned peers = __match_any_sync(0xFFFFFFFFu, key);
+    if (key >= 0 && (threadIdx.x & 31u) == (unsigned)(__ffs(peers) - 1)) atomicAdd(counters + key, (uint32_t)__popc(peers));
 }
 
 /* Rare path: the face is not trivially accepted. Sutherland-Hodgman in local
@@ -305,13 +316,15 @@ __global__ void __launch_bounds__(SETUP_THREADS) setup_kernel(PassParams p) {
         s_cta_base = total ? atomicAdd(p.tri_count + f, total) : 0u;
     }
     __syncthreads();
+    int key = -1;
     if (emit) {
         const uint32_t slot = s_cta_base + s_warp_total[wid] + (uint32_t)(incl - 1);
         if (slot < p.tri_cap) {
             store_triangle<SHADER>(p, f, slot, r, v, v + V2F_N, v + 2 * V2F_N);
-            count_single_tile(p, f, r);
+            key = single_tile_slot(p, r);
         }
     }
+    count_aggregated(p.tile_count + (size_t)f * p.tile_pad, key);
 }
 
 /* ---- scan: per frame, tile counts -> offsets into the pool + work queue ---- */
@@ -439,25 +452,35 @@ __global__ void __launch_bounds__(256) pairs_kernel(PassParams p) {
         const int local = k - __shfl_sync(FULL, excl, j);
         const int jtx0 = __shfl_sync(FULL, tx0, j), jty0 = __shfl_sync(FULL, ty0, j), jntx = __shfl_sync(FULL, ntx, j);
         const bool single = __shfl_sync(FULL, nt, j) == 1; /* a range inside one tile: the triangle touches it or covers nothing */
+        int key = -1, t = 0; /* key: counter slot of the pair's tile if the triangle can touch it */
+        float4 q0, q1;
+        const float4* rec = warp_rec + j * 4;
         if (k < total) {
-            const float4* rec = warp_rec + j * 4;
-            const float4 q0 = __ldg(rec), q1 = __ldg(rec + 1);
+            q0 = __ldg(rec);
+            q1 = __ldg(rec + 1);
             const int row = local / jntx;
             const int tx = jtx0 + (local - row * jntx), ty = jty0 + row;
-            const int t = ty * p.tiles_x + tx;
+            t = ty * p.tiles_x + tx;
             /* the same operands in both instantiations: the count and the fill agree */
-            if (single || tile_may_touch(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, (float)(tx * TILE), (float)(ty * TILE))) {
-                if (!FILL) {
-                    atomicAdd(cnt + tile_slot(p, t), 1u);
-                } else {
-                    const float4 q2 = __ldg(rec + 2), q3 = __ldg(rec + 3);
-                    const uint32_t s = atomicAdd(cur + tile_slot(p, t), 1u);
-                    float4* d = p.tile_recs + ((size_t)__ldg(to + t) + s) * 4;
-                    d[0] = q0;
-                    d[1] = q1;
-                    d[2] = q2;
-                    d[3] = q3;
-                }
+            if (single || tile_may_touch(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, (float)(tx * TILE), (float)(ty * TILE)))
+                key = tile_slot(p, t);
+        }
+        if (!FILL) {
+            if (key >= 0) atomicAdd(cnt + key, 1u); /* pairs of one round are mostly different tiles: not worth aggregating */
+        } else {
+            /* the lanes of a round that append to the same list (neighbouring small triangles) reserve their slots with ONE atomic */
+            const unsigned peers = __match_any_sync(FULL, key);
+            const int leader = __ffs(peers) - 1;
+            uint32_t s = 0;
+            if (key >= 0 && (int)lane == leader) s = atomicAdd(cur + key, (uint32_t)__popc(peers));
+            s = __shfl_sync(FULL, s, leader) + (uint32_t)__popc(peers & ((1u << lane) - 1u));
+            if (key >= 0) {
+                const float4 q2 = __ldg(rec + 2), q3 = __ldg(rec + 3);
+                float4* d = p.tile_recs + ((size_t)__ldg(to + t) + s) * 4;
+                d[0] = q0;
+                d[1] = q1;
+                d[2] = q2;
+                d[3] = q3;
             }
         }
     }
