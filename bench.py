@@ -35,8 +35,8 @@ FRAMES_PER_STEP = 256
 ORBIT = 1024
 SCENE = "african_head"
 # dram__bytes_read.sum + dram__bytes_write.sum of one raster_main launch (256 frames) in the committed ncu --set full
-# capture of this very command (profiles/r01_v4_step_kernels.md): 260.08 MB + 4.29 GB; per frame, scaled to the launch
-NCU_RASTER_MAIN_DRAM_BYTES_PER_FRAME = (260.08e6 + 4.29e9) / 256
+# capture of this very command (profiles/r01_v4_step_kernels.md): 259.78 MB + 4.29 GB; per frame, scaled to the launch
+NCU_RASTER_MAIN_DRAM_BYTES_PER_FRAME = (259.78e6 + 4.29e9) / 256
 T_BLINN = 7  # texel bytes per main-pass fragment: 3 (diffuse BGR) + 4 (shadow-map RGBA8 texel), SURVEY.md §8(d)
 METRIC = "frames/s at 1080p, shadowed Blinn (ShadowShader pass + BlinnShader pass), african_head orbit sweep"
 
