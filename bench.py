@@ -216,9 +216,12 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
     torch.cuda.set_device(local)
+    json_fd = None
     if world > 1:
-        # NCCL's own log lines (e.g. its version banner under NCCL_DEBUG=VERSION) go to stderr: stdout carries ONE JSON line
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        # stdout carries ONE JSON line: whatever a library prints there from now on (NCCL's version banner) goes to stderr
+        sys.stdout.flush()
+        json_fd = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     F = args.frames
     ctx = hana.Context(local)
@@ -391,7 +394,10 @@ def main():
             "kernel_ms_per_step": {k: v / args.steps for k, v in kernel_ms.items()},
             "cpu_baseline": cpu,
         }
-        print(json.dumps(line))
+        if json_fd is None:
+            print(json.dumps(line))
+        else:
+            os.write(json_fd, (json.dumps(line) + "\n").encode())
     for o in (sweep, sweep_b, model, dtex, ntex):
         o.close()
     ctx.close()
