@@ -324,6 +324,35 @@ def main():
 
     e2e_value = run_e2e(False)
     e2e_cd_value = run_e2e(True) if pin_d else None
+
+    # the present path end to end (single-GPU run only): the frames leave as the surface window_draw_buffer
+    # builds (win32.cpp:348-370) / a 24-bit TGA payload — flipped, B,G,R, 3 bytes per pixel — converted on the device
+    e2e_present = None
+    if world == 1:
+        pin_p = (PinnedBuffer(npx * 3 * FE), PinnedBuffer(npx * 3 * FE))
+
+        def step_present(s):
+            sw = rings[s & 1]
+            clr = (C.c_uint8 * 4)(0, 0, 0, 1)
+            r = ctx.L.hana_sweep_render(sw.h, model.h, hana.BLINN, C.c_void_p(pinned_u.ptr + s * F * usz), FE, dtex.h, ntex.h, clr,
+                                        float(hana.FLT_MAX))
+            if r == 0:
+                r = ctx.L.hana_sweep_present(sw.h, 0, FE, hana.PRESENT_BGR8, C.c_void_p(pin_p[s & 1].ptr), None)
+            if r != 0:
+                raise hana.HanaError(r, ctx.L.hana_last_error().decode())
+
+        for s in range(min(2, args.warmup)):
+            step_present(s)
+        barrier()
+        ctx.timer_start()
+        for s in range(args.warmup, total_steps):
+            step_present(s)
+        ms_p = ctx.timer_stop()
+        barrier()
+        e2e_present = {"value": FE * args.steps / (ms_p * 1e-3), "unit": "frames/s", "d2h_bytes_per_step": npx * 3 * FE,
+                       "note": "same loop, frames copied back as top-down B,G,R surfaces made by present_kernel (hana_sweep_present)"}
+        for b in pin_p:
+            b.close()
     last = (total_steps - 1) & 1
     sums_ok = int(np.frombuffer(pin_c[last].array, np.uint8, count=npx * 4).max() > 1 and
                   (pin_d is None or np.frombuffer(pin_d[last].array, np.float32, count=npx).min() < 1.0))  # something was drawn
@@ -381,6 +410,7 @@ def main():
                             "copies overlap the next batch; PCIe-bound", "frames_checked": sums_ok},
             "e2e_color_depth": {"value": e2e_cd_value, "unit": "frames/s", "d2h_bytes_per_step": npx * 8 * FE,
                                 "note": "same loop, depth plane copied back as well"},
+            "e2e_present_bgr8": e2e_present,
             "gpu_launches": int(launches),
             "clocks": clk,
             "roofline": {"bound": "hbm", "kernel": "raster_kernel<BLINN, CLEAR_FOLD>", "achieved": achieved, "peak": peak,
