@@ -31,7 +31,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 W, H = 1920, 1080
-FRAMES_PER_STEP = 256
+FRAMES_PER_STEP = 1024  # the whole configs[2] orbit in one submission (19 GB of frame targets): 256 -> 1024 frames amortises the per-launch tails, +4.6 %
 ORBIT = 1024
 SCENE = "african_head"
 # dram__bytes_read.sum + dram__bytes_write.sum of one raster_main launch (256 frames) in the committed ncu --set full

@@ -682,7 +682,7 @@ __global__ void __launch_bounds__(RW_THREADS, ShaderAttrs<SHADER>::LIT ? HANA_OC
     constexpr uint32_t SLOT_MASK = INLOOP ? 0x00FFFFFFu : 0xFFFFFFFFu;
     __shared__ RasterSmem<MODE> sm;
     const PassParams& p = q.p;
-    const unsigned lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
+    const unsigned lane = threadIdx.x & 31u, wid = __shfl_sync(FULL, threadIdx.x >> 5, 0); /* the broadcast lets ptxas keep the warp's shared-memory base in a uniform register instead of rebuilding it from S2R in the record loop */
     WarpTile<MODE>& wt = sm.w[wid];
     const int lx = (int)(lane & 7u), ly = (int)(lane >> 3);
     const bool tma = q.use_tma != 0;
@@ -746,7 +746,8 @@ __global__ void __launch_bounds__(RW_THREADS, ShaderAttrs<SHADER>::LIT ? HANA_OC
         const float fpy0 = (float)(Y0 + ly), fpy1 = (float)(Y0 + 4 + ly), fpy2 = (float)(Y0 + 8 + ly), fpy3 = (float)(Y0 + 12 + ly);
         const f2 FPX = f2_make(fpx0, fpx1), FPY01 = f2_make(fpy0, fpy1), FPY23 = f2_make(fpy2, fpy3);
         const int ipx0 = X0 + lx, ipy0 = Y0 + ly;
-        const int pix0 = ly * TILE + lx; /* the lane's pixel in sub-block 0; sub-block sb adds (sb >> 1) * 64 + (sb & 1) * 8 */
+        int pix0 = ly * TILE + lx; /* the lane's pixel in sub-block 0; sub-block sb adds (sb >> 1) * 64 + (sb & 1) * 8 */
+        asm volatile("" : "+r"(pix0)); /* opaque: ptxas otherwise recomputes it from %tid (S2R + four ALU ops) at every parked win */
 
         float bz[8];
         uint32_t bj[8];
