@@ -270,7 +270,10 @@ __device__ __noinline__ void setup_clipped(const PassParams& p, int f, int face,
 }
 
 template <int SHADER>
-__global__ void __launch_bounds__(SETUP_THREADS) setup_kernel(PassParams p) {
+/* `p` is __grid_constant__: the rare clipped path takes its address (a __noinline__ call), and without the qualifier
+ * every thread first copies all of PassParams to local memory. For the same reason the 39 vertex-stage floats are
+ * copied to a second array only on that path, so the common path keeps them in registers. */
+__global__ void __launch_bounds__(SETUP_THREADS) setup_kernel(const __grid_constant__ PassParams p) {
     const int f = blockIdx.y;
     const int face = blockIdx.x * SETUP_THREADS + threadIdx.x;
     const unsigned lane = threadIdx.x & 31u;
@@ -289,7 +292,10 @@ __global__ void __launch_bounds__(SETUP_THREADS) setup_kernel(PassParams p) {
         if (clip_trivial_accept(v)) {
             emit = triangle_setup(v, v + V2F_N, v + 2 * V2F_N, p.W, p.H, (uint32_t)face * 8u, r);
         } else {
-            setup_clipped<SHADER>(p, f, face, v);
+            float vc[3 * V2F_N];
+#pragma unroll
+            for (int k = 0; k < 3 * V2F_N; k++) vc[k] = v[k];
+            setup_clipped<SHADER>(p, f, face, vc);
         }
     }
     /* shuffle prefix sum over the emit flags per warp, warp totals combined in shared memory -> ONE slot-allocation
@@ -672,7 +678,7 @@ __device__ __forceinline__ uint32_t shade_fragment(const FragUniforms& fu, const
 
 template <int SHADER, int MODE>
 __global__ void __launch_bounds__(RW_THREADS, ShaderAttrs<SHADER>::LIT ? HANA_OCC_LIT : HANA_OCC_OTHER)
-    raster_kernel(RasterParams q, const __grid_constant__ CUtensorMap tm_color, const __grid_constant__ CUtensorMap tm_depth,
+    raster_kernel(const __grid_constant__ RasterParams q, const __grid_constant__ CUtensorMap tm_color, const __grid_constant__ CUtensorMap tm_depth,
                   const __grid_constant__ CUtensorMap tm_r8) {
     constexpr int NQ = ShaderAttrs<SHADER>::NQ;
     constexpr unsigned FULL = 0xFFFFFFFFu;
