@@ -1,15 +1,20 @@
 #!/usr/bin/env python
 """bench.py — the rasterisation hot path on N B200s, one JSON line on rank 0.
 
-A step = one batch of FRAMES_PER_STEP 1080p frames of BASELINE.json configs[1] (african_head, ShadowShader
-pass + Blinn pass, 1920x1080), each frame from the next camera of the configs[2] orbit (1024 cameras per turn,
-the reference's own Camera::update_transform). Frames are sharded over ranks in contiguous blocks of the orbit,
-no collective on the data path (weak scaling: every rank renders FRAMES_PER_STEP frames per step).
+Workload (BASELINE.json configs[1] frames on the configs[2] orbit): african_head, ShadowShader pass + BlinnShader pass,
+1920x1080, one frame per camera of the 1024-camera orbit (the reference's own Camera::update_transform). A step = ONE
+TURN OF THE ORBIT = 1024 frames in total, sharded over the ranks in contiguous blocks of 1024/N frames, no collective on
+the data path (strong scaling: the total work per step is fixed; `weak` in the line is the same loop with 1024 frames
+per rank). The scene is read from assets/ by the library's own OBJ/TGA readers; without it the bench fails.
 
-  value : frames/s, whole job, uniforms already resident in HBM, frames left in HBM (CUDA events, max over ranks)
-  e2e   : frames/s through the C ABI with HOST buffers: per step the uniforms go host->device from pinned memory
-          and every frame's colour + depth come back device->host into pinned memory, all inside the timed region
-  roofline     : the dominant kernel (raster_main), algorithmic bytes / its CUDA-event time, vs MEASURED_PEAKS.json
+  value    : frames/s, whole job, uniforms already resident in HBM, frames left in HBM (CUDA events, max over ranks)
+  e2e      : frames/s through the C ABI with HOST buffers: per step the uniforms go host->device from pinned memory and
+             every frame comes back device->host into pinned memory inside the timed region — as the RLE-compressed TGA
+             file the reference's own output path writes (TGAImage::write_tga_file, tgaimage.cpp:145-246; byte-identical),
+             packetised on the device. e2e_rgba8 / e2e_bgr8 are the same loop with raw colour planes.
+  parity   : after the timed loops every rank checks its frames with orbit index = 0 mod 64 against the CPU oracle
+             (outside the timed region): depth bits and coverage exact, colour within 1/255
+  roofline : the dominant kernel (raster_main), algorithmic bytes / its CUDA-event time, vs MEASURED_PEAKS.json
   cpu_baseline : the reference's own CPU pipeline (oracle/_ref, built from the unmodified sources) on the host cores
 
 --impl reference times only that CPU pipeline, with every host core, on a bounded sample of the same frames.
@@ -31,14 +36,20 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 W, H = 1920, 1080
-FRAMES_PER_STEP = 1024  # the whole configs[2] orbit in one submission (19 GB of frame targets): 256 -> 1024 frames amortises the per-launch tails, +4.6 %
-ORBIT = 1024
+ORBIT = 1024            # cameras per turn = frames per step over all ranks
 SCENE = "african_head"
-# dram__bytes_read.sum + dram__bytes_write.sum of one raster_main launch (256 frames) in the committed ncu --set full
-# capture of this very command (profiles/r01_v4_step_kernels.md): 259.78 MB + 4.29 GB; per frame, scaled to the launch
-NCU_RASTER_MAIN_DRAM_BYTES_PER_FRAME = (259.78e6 + 4.29e9) / 256
-T_BLINN = 7  # texel bytes per main-pass fragment: 3 (diffuse BGR) + 4 (shadow-map RGBA8 texel), SURVEY.md §8(d)
+NORMAL_PASS = 3         # the a2v stream of the reference's third walk over the model (after one warm-up frame), the one the oracle packs
+T_BLINN = 7             # texel bytes per main-pass fragment: 3 (diffuse BGR) + 4 (shadow-map RGBA8 texel), SURVEY.md §8(d)
 METRIC = "frames/s at 1080p, shadowed Blinn (ShadowShader pass + BlinnShader pass), african_head orbit sweep"
+PARITY_EVERY = 64
+
+
+def workload_config():
+    """The same dict in both arms."""
+    return {"workload": "configs[1] frames (african_head, ShadowShader + BlinnShader two-pass, 1920x1080) on the configs[2] "
+                        "orbit cameras: one step = one turn = 1024 frames over all ranks",
+            "scene": SCENE, "width": W, "height": H, "shader": "Blinn + shadow map", "orbit_frames": ORBIT,
+            "l2": "a step writes >= 2 GB of frame targets per GPU (>> 126 MB L2); mesh + textures (8.6 MB) are reused by design"}
 
 
 def env_int(name, default):
@@ -53,6 +64,11 @@ def host_cores():
         return max(1, len(os.sched_getaffinity(0)))
     except AttributeError:
         return max(1, os.cpu_count() or 1)
+
+
+def asset_dir():
+    d = os.path.join(ROOT, "assets")
+    return d if os.path.exists(os.path.join(d, SCENE, SCENE + ".obj")) else None
 
 
 # ----------------------------------------------------------------------------- reference / cpu baseline
@@ -73,11 +89,11 @@ def _ref_worker(args):
 
 
 def _port_worker(args):
-    pack, first, count, orbit = args
+    assets, first, count, orbit = args
     import __graft_entry__ as ge
     hana = ge.load_package()
     from oracle import horacle as Hh
-    sc = hana.load_hscene(pack) if pack else hana.synthetic_scene("blob", tex=1024)
+    sc = hana.load_bundled(SCENE, assets, NORMAL_PASS)
     port = Hh.Port()
     arr = hana.orbit_sweep_uniforms(W, H, first, count, frames_per_turn=orbit)
     t = 0.0
@@ -90,22 +106,22 @@ def _port_worker(args):
 
 
 def cpu_frames_per_s(frames_per_core, first_frame=0):
-    """Frame-sharded run of the CPU pipeline over all host cores. Returns (frames/s, kind, cores, sample)."""
+    """Frame-sharded run of the CPU pipeline over all host cores. Returns (frames/s, kind, cores, sample, s/frame/core)."""
     cores = host_cores()
-    obj = os.path.join(ROOT, "oracle", "_ref", "assets", SCENE, SCENE + ".obj")
-    pack = os.path.join(ROOT, "oracle", "_ref", "assets", SCENE + ".npz")
-    use_ref = os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libhana_ref.so")) and os.path.exists(obj)
+    assets = asset_dir()
+    if assets is None:
+        raise SystemExit("bench.py: assets/%s is missing (run __graft_entry__.build() where /root/reference exists)" % SCENE)
+    obj = os.path.join(assets, SCENE, SCENE + ".obj")
+    use_ref = os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libhana_ref.so"))
     stride = ORBIT // cores if cores <= ORBIT else 1
-    jobs = [((obj if use_ref else (pack if os.path.exists(pack) else None)), (first_frame + i * stride) % ORBIT, frames_per_core,
-             ORBIT) for i in range(cores)]
+    jobs = [((obj if use_ref else assets), (first_frame + i * stride) % ORBIT, frames_per_core, ORBIT) for i in range(cores)]
     ctx = mp.get_context("spawn")
     t0 = time.perf_counter()
     with ctx.Pool(cores) as pool:
         busy = pool.map(_ref_worker if use_ref else _port_worker, jobs)
     wall = time.perf_counter() - t0
     n = cores * frames_per_core
-    # throughput of the parallel section: every core renders its block concurrently; the slowest core bounds it
-    fps = n / max(busy)
+    fps = n / max(busy)  # every core renders its block concurrently; the slowest core bounds the parallel section
     kind = "reference" if use_ref else "port"
     sample = "%d frames of the orbit (%d per core x %d cores, DrawModel::draw only: both passes + shadow clear), wall %.1fs" % (
         n, frames_per_core, cores, wall)
@@ -127,10 +143,10 @@ def run_reference(args, rank):
     _, kind, cores, sample, sec_per_frame_core = info
     line = {
         "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * cores * per_core / fps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "bundled african_head scene, orbit cameras",
-        "config": {"workload": "configs[1] frames (african_head, Shadow+Blinn two-pass, 1920x1080) on the configs[2] orbit cameras; "
-                               "CPU reference, frame-sharded over host cores", "frames_per_step": cores * per_core},
+        "warmup": args.warmup, "ms_per_step": 1e3 * cores * per_core / fps, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32", "data": "bundled african_head mesh + textures (reference assets), synthetic orbit cameras",
+        "config": workload_config(),
+        "run": {"frames_per_step": cores * per_core, "arm": "CPU reference, frame-sharded over host cores"},
         "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": kind, "sample": sample,
                          "single_core_ms_per_frame": 1e3 * sec_per_frame_core},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -191,6 +207,40 @@ class ClockSampler:
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def bind_near_gpu(torch, local):
+    """Run this rank (and first-touch its pinned rings) on the CPUs of the GPU's NUMA node. Returns (old affinity, note)."""
+    try:
+        old = os.sched_getaffinity(0)
+        p = torch.cuda.get_device_properties(local)
+        bdf = "%04x:%02x:%02x.0" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
+        txt = open("/sys/bus/pci/devices/%s/local_cpulist" % bdf).read().strip()
+        cpus = set()
+        for part in txt.split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        cpus &= old
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            node = open("/sys/bus/pci/devices/%s/numa_node" % bdf).read().strip()
+            return old, "rank bound to the %d CPUs of the GPU's NUMA node %s while its pinned rings are allocated" % (len(cpus), node)
+        return old, "GPU-local CPU list is outside this process's affinity mask: not bound"
+    except (OSError, AttributeError, ValueError) as e:
+        return None, "not bound (%s)" % type(e).__name__
+
+
+def raster_main_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per raster_main launch from the committed ncu --set full capture of
+    THIS build (profiles/raster_main_dram.json, written by tools/ncu_summary.py --traffic); None if there is none."""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "raster_main_dram.json")))
+        return d
+    except (OSError, ValueError):
+        return None
+
+
 # ----------------------------------------------------------------------------- GPU arm
 def main():
     ap = argparse.ArgumentParser()
@@ -198,8 +248,10 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="hana")
-    ap.add_argument("--frames", type=int, default=FRAMES_PER_STEP)
+    ap.add_argument("--frames", type=int, default=0, help="frames per rank and step (default: 1024 / ranks)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip configs[3]/[4], the README workload and the latency record")
+    ap.add_argument("--no-weak", action="store_true", help="N > 1: skip the extra weak-scaling loop")
     args = ap.parse_args()
     rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
     if args.impl == "reference":
@@ -215,6 +267,10 @@ def main():
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
+    assets = asset_dir()
+    if assets is None:
+        raise SystemExit("bench.py: assets/%s/%s.obj is missing — the bench measures the bundled scene and nothing else "
+                         "(run __graft_entry__.build() where /root/reference exists)" % (SCENE, SCENE))
     torch.cuda.set_device(local)
     json_fd = None
     if world > 1:
@@ -223,28 +279,29 @@ def main():
         json_fd = os.dup(1)
         os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    F = args.frames
+    old_affinity, numa_note = bind_near_gpu(torch, local)
+    F = args.frames if args.frames > 0 else max(1, ORBIT // world)
     ctx = hana.Context(local)
-    pack = os.path.join(ROOT, "oracle", "_ref", "assets", SCENE + ".npz")
-    if os.path.exists(pack):
-        scene, data = hana.load_hscene(pack), "bundled african_head mesh + textures (reference assets), synthetic orbit cameras"
-    else:
-        scene, data = hana.synthetic_scene("blob", tex=1024), "synthetic sphere scene (bundled assets not packed on this box)"
+    scene = hana.load_bundled(SCENE, assets, NORMAL_PASS)  # hana_obj_load + hana_tga_load
+    data = "bundled african_head mesh + textures (reference assets, read by hana_obj_load/hana_tga_load), synthetic orbit cameras"
     model, dtex, ntex = scene.upload(ctx)
     sweep = ctx.sweep(W, H, F)
 
-    # this rank's contiguous block of the orbit; step s renders frames [s*F, (s+1)*F) of the block (cyclic)
-    block = ORBIT // world
-    first = rank * block
+    # this rank's contiguous block of the orbit: every step renders frames [first, first + F)
+    first = (rank * F) % ORBIT
     total_steps = args.warmup + args.steps
     usz = C.sizeof(HanaUniforms)
-    pinned_u = PinnedBuffer(usz * F * total_steps)
-    for s in range(total_steps):
-        arr = hana.orbit_sweep_uniforms(W, H, first + (s * F) % block, F, frames_per_turn=ORBIT)
-        C.memmove(pinned_u.ptr + s * F * usz, arr, usz * F)
-    u_dev = torch.empty(usz * F * total_steps, dtype=torch.uint8, device="cuda")
+    block_u = hana.orbit_sweep_uniforms(W, H, first, F, frames_per_turn=ORBIT)
+    pinned_u = PinnedBuffer(usz * F)
+    C.memmove(pinned_u.ptr, block_u, usz * F)
+    u_dev = torch.empty(usz * F, dtype=torch.uint8, device="cuda")
     u_dev.copy_(torch.from_numpy(pinned_u.array))
     torch.cuda.synchronize()
+    clr = (C.c_uint8 * 4)(0, 0, 0, 1)
+
+    def ck(r):
+        if r != 0:
+            raise hana.HanaError(r, ctx.L.hana_last_error().decode())
 
     def barrier():
         ctx.sync()
@@ -252,170 +309,250 @@ def main():
         if world > 1:
             dist.barrier()
 
-    def step_resident(s):
-        clr = (C.c_uint8 * 4)(0, 0, 0, 1)
-        r = ctx.L.hana_sweep_render_dev(sweep.h, model.h, hana.BLINN, C.c_void_p(u_dev.data_ptr() + s * F * usz), 1, F, dtex.h, ntex.h,
-                                        clr, float(hana.FLT_MAX))
-        if r != 0:
-            raise hana.HanaError(r, ctx.L.hana_last_error().decode())
+    def max_over_ranks(ms):
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(vals):
+        t = torch.tensor(vals, dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return [float(x) for x in t.tolist()]
+
+    def timed_resident(sw, n_frames, udev_ptr, steps, warmup):
+        for _ in range(warmup):
+            ck(ctx.L.hana_sweep_render_dev(sw.h, model.h, hana.BLINN, C.c_void_p(udev_ptr), 1, n_frames, dtex.h, ntex.h, clr,
+                                           float(hana.FLT_MAX)))
+        barrier()
+        ctx.timer_start()
+        for _ in range(steps):
+            ck(ctx.L.hana_sweep_render_dev(sw.h, model.h, hana.BLINN, C.c_void_p(udev_ptr), 1, n_frames, dtex.h, ntex.h, clr,
+                                           float(hana.FLT_MAX)))
+        ms = ctx.timer_stop()
+        barrier()
+        return ms
 
     # ---- value: device-resident inputs, frames stay in HBM
-    for s in range(args.warmup):
-        step_resident(s)
+    for w in range(args.warmup):
+        ck(ctx.L.hana_sweep_render_dev(sweep.h, model.h, hana.BLINN, C.c_void_p(u_dev.data_ptr()), 1, F, dtex.h, ntex.h, clr,
+                                       float(hana.FLT_MAX)))
+        if w == 0:
+            ctx.sync()  # the first batch of a context sizes the scratch (and is rendered again if it ran out)
     barrier()
+    overflow0 = sweep.overflow_count()
     ctx.profile(os.environ.get("HANA_BENCH_NOPROF") != "1", reset=True)
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
     l0 = ctx.launches
     ctx.timer_start()
-    for s in range(args.warmup, total_steps):
-        step_resident(s)
+    for _ in range(args.steps):
+        ck(ctx.L.hana_sweep_render_dev(sweep.h, model.h, hana.BLINN, C.c_void_p(u_dev.data_ptr()), 1, F, dtex.h, ntex.h, clr,
+                                       float(hana.FLT_MAX)))
     ms = ctx.timer_stop()
     barrier()
     clk = clocks.stop() if rank == 0 else None
     launches = ctx.launches - l0
     prof = ctx.profile_get()
     ctx.profile(False, reset=False)
-    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = float(t.item())
+    overflow_batches = sweep.overflow_count() - overflow0  # batches of the timed region that dropped work: must be 0
+    ms_max = max_over_ranks(ms)
     frames_total = F * args.steps * world
     value = frames_total / (ms_max * 1e-3)
 
-    # ---- e2e: host uniforms in (pinned), every frame's colour buffer out (pinned), inside the timed region.
-    # What DrawModel::draw hands back to its caller is the colour buffer (window_draw_buffer reads nothing else,
-    # win32.cpp:361; the depth buffer never leaves the renderer), so that is what the headline e2e copies back; the
-    # same loop with the depth plane as well is reported beside it. Two frame rings alternate so that the copies of
-    # batch k (copy stream) overlap the kernels of batch k+1.
-    # The copies are PCIe-bound whatever the batch size, so the e2e loop submits at most 128 frames per step: that bounds
-    # the pinned host memory at 2.1 GB per rank (8 ranks share one host), plus as much again for the depth variant,
-    # which only the single-GPU run measures.
+    # ---- parity of the frames just timed: every rank, its frames with orbit index = 0 mod PARITY_EVERY, vs the CPU oracle
+    from oracle import horacle as Hh  # the checker, outside every timed region
+    port = Hh.Port()
+    par = {"frames_checked": 0, "frames_failed": 0, "coverage_mismatch_px": 0, "depth_bits_mismatch_px": 0,
+           "colour_maxdiff": 0, "colour_mismatch_px": 0}
+    frag_main_s, frag_all_s = [], []
+    for k in range(first, first + F):
+        if k % PARITY_EVERY:
+            continue
+        hu = Hh.HanaUniforms.from_bytes(block_u[k - first].to_bytes())
+        r = port.draw_model(Hh.BLINN, hu, scene.a2v, W, H, diffuse=scene.diffuse, normal=scene.normal, want_counters=True)
+        frag_main_s.append(r["counters"][1]["zpass"])
+        frag_all_s.append(r["counters"][0]["zpass"] + r["counters"][1]["zpass"])
+        gcol, gdep = sweep.download(k - first)
+        cov = int(((gdep != hana.FLT_MAX) != (r["depth"] != hana.FLT_MAX)).sum())
+        dbits = int((gdep.view(np.uint32) != r["depth"].view(np.uint32)).sum())
+        dc = np.abs(gcol[..., :3].astype(np.int16) - r["color"][..., :3].astype(np.int16))
+        par["frames_checked"] += 1
+        par["coverage_mismatch_px"] += cov
+        par["depth_bits_mismatch_px"] += dbits
+        par["colour_maxdiff"] = max(par["colour_maxdiff"], int(dc.max()))
+        par["colour_mismatch_px"] += int((dc > 0).any(-1).sum())
+        if cov or dbits or dc.max() > 1:
+            par["frames_failed"] += 1
+    sums = sum_over_ranks([par["frames_checked"], par["frames_failed"], par["coverage_mismatch_px"], par["depth_bits_mismatch_px"],
+                           par["colour_mismatch_px"], sum(frag_main_s), sum(frag_all_s), overflow_batches])
+    cmax = max_over_ranks(par["colour_maxdiff"])
+    parity = {"frames_checked": int(sums[0]), "mismatches": int(sums[1]), "coverage_mismatch_px": int(sums[2]),
+              "depth_bits_mismatch_px": int(sums[3]), "colour_mismatch_px": int(sums[4]), "colour_maxdiff": int(cmax),
+              "every": PARITY_EVERY, "oracle": "oracle/hana_oracle.c (C port, pinned bit-exact to the reference)",
+              "bars": "coverage and depth bits exact, colour <= 1/255 per channel"}
+    frag_main = sums[5] / max(sums[0], 1) if sums[0] else 436951.0
+    frag_all = sums[6] / max(sums[0], 1) if sums[0] else 997805.0
+    overflow_total = int(sums[7])
+
+    # ---- weak-scaling figure beside it (N > 1): every rank renders a whole turn per step
+    weak = None
+    if world > 1 and not args.no_weak:
+        FW = ORBIT
+        sweep.close()
+        sweep = ctx.sweep(W, H, FW)
+        arr = hana.orbit_sweep_uniforms(W, H, first, FW, frames_per_turn=ORBIT)
+        pu = PinnedBuffer(usz * FW)
+        C.memmove(pu.ptr, arr, usz * FW)
+        ud = torch.empty(usz * FW, dtype=torch.uint8, device="cuda")
+        ud.copy_(torch.from_numpy(pu.array))
+        torch.cuda.synchronize()
+        wsteps = max(3, args.steps // 4)
+        ck(ctx.L.hana_sweep_render_dev(sweep.h, model.h, hana.BLINN, C.c_void_p(ud.data_ptr()), 1, FW, dtex.h, ntex.h, clr,
+                                       float(hana.FLT_MAX)))
+        ctx.sync()
+        ow0 = sweep.overflow_count()
+        wms = max_over_ranks(timed_resident(sweep, FW, ud.data_ptr(), wsteps, 3))
+        weak = {"value": FW * wsteps * world / (wms * 1e-3), "unit": "frames/s", "frames_per_rank_and_step": FW, "steps": wsteps,
+                "scaling": "weak"}
+        overflow_total += sweep.overflow_count() - ow0
+        pu.close()
+        del ud
+        sweep.close()
+        sweep = ctx.sweep(W, H, F)
+
+    # ---- e2e: host uniforms in (pinned), every frame out (pinned), inside the timed region; two rings alternate so that
+    # the copies of batch k (copy stream) overlap the kernels of batch k+1. At most 128 frames per submission: bounds the
+    # pinned host memory per rank (8 ranks share one host).
     npx = W * H
     FE = min(F, 128)
     sweep_b = ctx.sweep(W, H, FE)
     rings = (sweep, sweep_b)
-    pin_c = (PinnedBuffer(npx * 4 * FE), PinnedBuffer(npx * 4 * FE))
-    pin_d = (PinnedBuffer(npx * 4 * FE), PinnedBuffer(npx * 4 * FE)) if world == 1 else None
+    e2e_steps = args.steps * max(1, F // FE)  # the same number of frames as the value loop
 
-    def step_e2e(s, with_depth):
-        sw = rings[s & 1]
-        clr = (C.c_uint8 * 4)(0, 0, 0, 1)
-        r = ctx.L.hana_sweep_render(sw.h, model.h, hana.BLINN, C.c_void_p(pinned_u.ptr + s * F * usz), FE, dtex.h, ntex.h, clr,
-                                    float(hana.FLT_MAX))
-        if r != 0:
-            raise hana.HanaError(r, ctx.L.hana_last_error().decode())
-        sw.download_async(0, FE, pin_c[s & 1].ptr, pin_d[s & 1].ptr if with_depth else None)
+    def render_host(sw):
+        ck(ctx.L.hana_sweep_render(sw.h, model.h, hana.BLINN, C.c_void_p(pinned_u.ptr), FE, dtex.h, ntex.h, clr, float(hana.FLT_MAX)))
 
-    def run_e2e(with_depth):
-        for s in range(min(2, args.warmup)):
-            step_e2e(s, with_depth)
+    def run_e2e(step_fn):
+        for s in range(2):
+            step_fn(s)
         barrier()
         ctx.timer_start()
-        for s in range(args.warmup, total_steps):
-            step_e2e(s, with_depth)
+        for s in range(e2e_steps):
+            step_fn(s)
         ms_ = ctx.timer_stop()  # waits for every render and every copy
         barrier()
-        t_ = torch.tensor([ms_], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(t_, op=dist.ReduceOp.MAX)
-        return FE * args.steps * world / (float(t_.item()) * 1e-3)
+        return FE * e2e_steps * world / (max_over_ranks(ms_) * 1e-3)
 
-    e2e_value = run_e2e(False)
-    e2e_cd_value = run_e2e(True) if pin_d else None
+    # (a) raw RGBA8 colour planes, what DrawModel::draw's caller reads (win32.cpp:361)
+    pin_c = (PinnedBuffer(npx * 4 * FE), PinnedBuffer(npx * 4 * FE))
 
-    # the present path end to end (single-GPU run only): the frames leave as the surface window_draw_buffer
-    # builds (win32.cpp:348-370) / a 24-bit TGA payload — flipped, B,G,R, 3 bytes per pixel — converted on the device
-    e2e_present = None
-    if world == 1:
-        pin_p = (PinnedBuffer(npx * 3 * FE), PinnedBuffer(npx * 3 * FE))
+    def step_rgba(s):
+        render_host(rings[s & 1])
+        rings[s & 1].download_async(0, FE, pin_c[s & 1].ptr, None)
 
-        def step_present(s):
+    e2e_rgba = run_e2e(step_rgba)
+    rgba_ok = int(np.frombuffer(pin_c[(e2e_steps - 1) & 1].array, np.uint8, count=npx * 4).max() > 1)
+    for b in pin_c:
+        b.close()
+    # (b) the surface window_draw_buffer builds (win32.cpp:348-370): flipped, B,G,R, 3 bytes per pixel, converted on the device
+    pin_p = (PinnedBuffer(npx * 3 * FE), PinnedBuffer(npx * 3 * FE))
+
+    def step_bgr(s):
+        render_host(rings[s & 1])
+        ck(ctx.L.hana_sweep_present(rings[s & 1].h, 0, FE, hana.PRESENT_BGR8, C.c_void_p(pin_p[s & 1].ptr), None))
+
+    e2e_bgr = run_e2e(step_bgr)
+    # (c) RLE TGA files (tgaimage.cpp:206-246 packets, byte-identical to hana_tga_write), packetised on the device
+    e2e_tga, tga_info = None, None
+    if hasattr(ctx.L, "hana_sweep_encode_tga"):
+        cap = npx * 3 * FE  # the pinned ring is as large as the raw surfaces; an RLE file of these frames is ~5x smaller
+        offs = ((C.c_uint64 * (FE + 1))(), (C.c_uint64 * (FE + 1))())
+
+        def step_tga(s):
             sw = rings[s & 1]
-            clr = (C.c_uint8 * 4)(0, 0, 0, 1)
-            r = ctx.L.hana_sweep_render(sw.h, model.h, hana.BLINN, C.c_void_p(pinned_u.ptr + s * F * usz), FE, dtex.h, ntex.h, clr,
-                                        float(hana.FLT_MAX))
-            if r == 0:
-                r = ctx.L.hana_sweep_present(sw.h, 0, FE, hana.PRESENT_BGR8, C.c_void_p(pin_p[s & 1].ptr), None)
-            if r != 0:
-                raise hana.HanaError(r, ctx.L.hana_last_error().decode())
+            render_host(sw)
+            ck(ctx.L.hana_sweep_encode_tga(sw.h, 0, FE, 1))
+            ck(ctx.L.hana_sweep_fetch_tga(sw.h, C.c_void_p(pin_p[s & 1].ptr), C.c_size_t(cap), offs[s & 1]))
 
-        for s in range(min(2, args.warmup)):
-            step_present(s)
-        barrier()
-        ctx.timer_start()
-        for s in range(args.warmup, total_steps):
-            step_present(s)
-        ms_p = ctx.timer_stop()
-        barrier()
-        e2e_present = {"value": FE * args.steps / (ms_p * 1e-3), "unit": "frames/s", "d2h_bytes_per_step": npx * 3 * FE,
-                       "note": "same loop, frames copied back as top-down B,G,R surfaces made by present_kernel (hana_sweep_present)"}
-        for b in pin_p:
-            b.close()
-    last = (total_steps - 1) & 1
-    sums_ok = int(np.frombuffer(pin_c[last].array, np.uint8, count=npx * 4).max() > 1 and
-                  (pin_d is None or np.frombuffer(pin_d[last].array, np.float32, count=npx).min() < 1.0))  # something was drawn
+        e2e_tga = run_e2e(step_tga)
+        last = (e2e_steps - 1) & 1
+        total_bytes = int(offs[last][FE])
+        # byte-identity of one delivered file with the host writer (outside the timed region)
+        import tempfile
+        f0 = bytes(pin_p[last].array[int(offs[last][0]):int(offs[last][1])])
+        gcol, _ = rings[last].download(0)
+        with tempfile.TemporaryDirectory() as td:
+            pth = os.path.join(td, "f.tga")
+            hana.tga_write(pth, np.ascontiguousarray(gcol[::-1, :, 2::-1]), rle=True)
+            same = open(pth, "rb").read() == f0
+        tga_info = {"bytes_per_frame": total_bytes / FE, "file0_identical_to_hana_tga_write": bool(same)}
+    for b in pin_p:
+        b.close()
 
     if rank == 0:
-        peaks, peak_src = None, "fallback"
+        if old_affinity:
+            os.sched_setaffinity(0, old_affinity)  # the CPU legs below use every host core
+        peak_src = "fallback (B200_PROFILING.md)"
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
             peak, peak_src = float(peaks["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
         except (OSError, KeyError, ValueError):
             peak = 6650.0
-        # reference-equivalent fragment counts: sampled with the instrumented CPU port
         cpu = None
-        frag_main = frag_all = None
         if world == 1 and not args.no_cpu_baseline:
-            from oracle import horacle as Hh
-            port = Hh.Port()
-            fm, fa = [], []
-            for k in (0, 256, 512, 768):
-                u = Hh.HanaUniforms.from_bytes(hana.orbit_sweep_uniforms(W, H, k, 1, frames_per_turn=ORBIT)[0].to_bytes())
-                r = port.draw_model(Hh.BLINN, u, scene.a2v, W, H, diffuse=scene.diffuse, normal=scene.normal, want_counters=True)
-                fm.append(r["counters"][1]["zpass"])
-                fa.append(r["counters"][0]["zpass"] + r["counters"][1]["zpass"])
-            frag_main, frag_all = statistics.mean(fm), statistics.mean(fa)
             fps, kind, cores, sample, spf = cpu_frames_per_s(4)  # 4 frames per core: ~13 core-seconds of the reference on 16 cores
             cpu = {"value": fps, "unit": "frames/s", "cores": cores, "kind": kind, "sample": sample,
                    "single_core_ms_per_frame": 1e3 * spf}
-        if frag_main is None:
-            frag_main, frag_all = 436951.0, 997805.0  # camera 0 of the orbit
+        extras = None
+        if world == 1 and not args.no_extras:
+            sweep.close()
+            sweep_b.close()
+            extras = run_extras(hana, ctx, peak, assets)
+            sweep = sweep_b = None
         ncorner = scene.a2v.shape[0]
         bytes_frame = 2 * (ncorner * 32 + npx * 8) + frag_main * T_BLINN          # whole frame, both passes
         bytes_raster_main = npx * 8 + frag_main * T_BLINN                        # the dominant kernel's share
         rm_ms, rm_n = prof["raster_main"]
         per_launch_ms = rm_ms / max(rm_n, 1)
-        achieved = bytes_raster_main * F / (per_launch_ms * 1e-3) / 1e9
+        achieved = bytes_raster_main * F / (per_launch_ms * 1e-3) / 1e9 if rm_n else None
         kernel_ms = {k: v[0] for k, v in prof.items()}
-        gpu_ms_step = sum(kernel_ms.values()) / args.steps
+        traffic = raster_main_traffic()
+        if e2e_tga is not None:
+            e2e = {"value": e2e_tga, "unit": "frames/s", "frames_per_step": FE, "steps": e2e_steps, "h2d_bytes_per_step": usz * FE,
+                   "d2h_bytes_per_step": tga_info["bytes_per_frame"] * FE + 8 * (FE + 1), "delivered": "RLE TGA files",
+                   "file0_identical_to_hana_tga_write": tga_info["file0_identical_to_hana_tga_write"],
+                   "note": "hana_sweep_render from pinned host uniforms; every frame comes back to pinned host memory as the "
+                           "RLE-compressed 24-bit TGA file TGAImage::write_tga_file(rle=true) would write (tgaimage.cpp:145-246), "
+                           "packetised on the device (hana_sweep_encode_tga), two rings so copies overlap the next batch"}
+        else:
+            e2e = {"value": e2e_bgr, "unit": "frames/s", "frames_per_step": FE, "steps": e2e_steps, "h2d_bytes_per_step": usz * FE,
+                   "d2h_bytes_per_step": npx * 3 * FE, "delivered": "top-down B,G,R surfaces (hana_sweep_present)"}
         line = {
             "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": data,
-            "config": {"workload": "configs[1] frames (african_head, Shadow+Blinn two-pass, 1920x1080) on the configs[2] orbit cameras, "
-                                   "batched %d frames per submission" % F,
-                       "frames_per_step": F, "width": W, "height": H, "faces": ncorner // 3, "orbit_frames": ORBIT,
-                       "sharding": "contiguous orbit blocks per rank, no collective",
-                       "l2": "per-step footprint %.2f GB of frame targets >> 126 MB L2; mesh + textures (%.1f MB) are reused by "
-                             "design" % (F * npx * 9 / 1e9, (ncorner * 32 + 2 * 4 * 1024 * 1024) / 1e6),
-                       "tma": bool(ctx.uses_tma)},
+            "config": workload_config(),
+            "run": {"frames_per_step_total": F * world, "frames_per_rank_and_step": F, "faces": ncorner // 3,
+                    "sharding": "contiguous orbit blocks per rank, no collective", "tma": bool(ctx.uses_tma), "numa": numa_note},
             "mfrag_per_s": value * frag_all / 1e6, "mtri_per_s": value * 2 * (ncorner // 3) / 1e6,
-            "us_per_frame": 1e6 / value * world,
-            "e2e": {"value": e2e_value, "unit": "frames/s", "frames_per_step": FE, "h2d_bytes_per_step": usz * FE,
-                    "d2h_bytes_per_step": npx * 4 * FE,
-                    "note": "hana_sweep_render from pinned host uniforms + the colour buffer of every frame (what "
-                            "DrawModel::draw's caller reads, win32.cpp:361) copied back to pinned host memory, two rings so "
-                            "copies overlap the next batch; PCIe-bound", "frames_checked": sums_ok},
-            "e2e_color_depth": {"value": e2e_cd_value, "unit": "frames/s", "d2h_bytes_per_step": npx * 8 * FE,
-                                "note": "same loop, depth plane copied back as well"},
-            "e2e_present_bgr8": e2e_present,
+            "us_per_frame_per_gpu": 1e6 / value * world,
+            "parity": parity,
+            "overflow_batches": overflow_total,
+            "weak": weak,
+            "e2e": e2e,
+            "e2e_rgba8": {"value": e2e_rgba, "unit": "frames/s", "d2h_bytes_per_step": npx * 4 * FE, "something_drawn": rgba_ok,
+                          "note": "same loop, raw RGBA8 colour planes (what DrawModel::draw's caller reads, win32.cpp:361); PCIe-bound"},
+            "e2e_bgr8": {"value": e2e_bgr, "unit": "frames/s", "d2h_bytes_per_step": npx * 3 * FE,
+                         "note": "same loop, top-down B,G,R surfaces made by present_kernel (hana_sweep_present)"},
             "gpu_launches": int(launches),
             "clocks": clk,
             "roofline": {"bound": "hbm", "kernel": "raster_kernel<BLINN, CLEAR_FOLD>", "achieved": achieved, "peak": peak,
-                         "unit": "GB/s", "frac": achieved / peak, "traffic": NCU_RASTER_MAIN_DRAM_BYTES_PER_FRAME * F,
-                         "traffic_source": "ncu --set full capture under profiles/ (dram bytes read + written per launch)",
+                         "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
+                         "traffic": (traffic["bytes_per_frame"] * F) if traffic else None,
+                         "traffic_source": (traffic.get("source") if traffic else "no ncu --set full capture of this build committed"),
                          "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": bytes_raster_main * F, "ms_per_launch": per_launch_ms},
             "frame_roofline": {"algorithmic_bytes_per_frame": bytes_frame, "achieved": bytes_frame * value / world / 1e9,
@@ -424,16 +561,121 @@ def main():
             "kernel_ms_per_step": {k: v / args.steps for k, v in kernel_ms.items()},
             "cpu_baseline": cpu,
         }
+        if extras:
+            line.update(extras)
         if json_fd is None:
             print(json.dumps(line))
         else:
             os.write(json_fd, (json.dumps(line) + "\n").encode())
     for o in (sweep, sweep_b, model, dtex, ntex):
-        o.close()
+        if o is not None:
+            o.close()
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
+    if parity["mismatches"] or overflow_total:
+        sys.stderr.write("bench.py: PARITY FAILURE or dropped batches: %s overflow=%d\n" % (parity, overflow_total))
+        return 3
     return 0
+
+
+def run_extras(hana, ctx, peak, assets):
+    """Rank 0 of a single-GPU run, outside every timed region of the headline: BASELINE.json configs[3] and configs[4] at
+    their stated size (ms per frame + SURVEY.md §8(d) roofline fraction), the reference's only published workload
+    (README.md:5: diablo3_pose, NormalMapShader + shadow, 1000x600, 27 fps on the author's PC), and the single-frame
+    latency of the host-buffer entry point (hana_draw_model_host, what the drop-in shim calls)."""
+    out = {}
+    try:
+        g = np.load(os.path.join(ROOT, "tests", "golden", "configs_full_golden.npz"))
+    except OSError:
+        g = None
+
+    def time_single(sc, shader, w, h, reps):
+        objs = sc.upload(ctx)
+        u = hana.default_uniforms(w, h, True)
+        sw = ctx.sweep(w, h, 1)
+        for _ in range(2):
+            sw.render(objs[0], shader, [u], objs[1], objs[2])
+        ctx.sync()
+        ctx.profile(True, reset=True)
+        ctx.timer_start()
+        for _ in range(reps):
+            sw.render(objs[0], shader, [u], objs[1], objs[2])
+        ms = ctx.timer_stop() / reps
+        prof = {k: v[0] / reps for k, v in ctx.profile_get().items()}
+        ctx.profile(False, reset=False)
+        for o in (sw,) + tuple(objs):
+            o.close()
+        return ms, prof
+
+    # configs[3]: 10 M tiny triangles at 3840x2160, Blinn + shadow
+    a2v = hana.scene.synthetic_grid(2237, 2237, seed=1234)
+    dif, nm = hana.scene.noise_textures(1234, 1024, flat_normal=True)
+    ms, prof = time_single(hana.Scene("c4", a2v, dif, nm), hana.BLINN, 3840, 2160, 5)
+    nfrag = float(g["c4_zpass"][1]) if g is not None else 3840 * 2160 * 0.95
+    b = 2 * (a2v.shape[0] * 32 + 3840 * 2160 * 8) + nfrag * T_BLINN
+    out["c4"] = {"config": "configs[3]: 9 999 392 triangles, 3840x2160, Blinn + shadow, one frame per submission", "ms_per_frame": ms,
+                 "mtri_per_s": 2 * (a2v.shape[0] // 3) / ms / 1e3, "algorithmic_bytes": b, "frac": b / (ms * 1e-3) / 1e9 / peak,
+                 "kernel_ms": prof}
+    del a2v
+    # configs[4]: 9 216 large triangles, depth complexity ~8, 7680x4320, NormalMap + shadow
+    a2v = hana.scene.synthetic_layers(8, 32, 18, seed=99)
+    dif, nm = hana.scene.noise_textures(99, 1024)
+    ms, prof = time_single(hana.Scene("c5", a2v, dif, nm), hana.NORMALMAP, 7680, 4320, 5)
+    nfrag = float(g["c5_zpass"][1]) if g is not None else 7680 * 4320 * 7.7
+    b = 2 * (a2v.shape[0] * 32 + 7680 * 4320 * 8) + nfrag * (T_BLINN + 3)
+    out["c5"] = {"config": "configs[4]: 9 216 triangles, depth complexity ~8, 7680x4320, NormalMap + shadow, one frame per submission",
+                 "ms_per_frame": ms, "mfrag_per_s": nfrag / ms / 1e3, "algorithmic_bytes": b, "frac": b / (ms * 1e-3) / 1e9 / peak,
+                 "kernel_ms": prof}
+    # the README workload: diablo3_pose, NormalMap + shadow, 1000x600
+    try:
+        dia = hana.load_bundled("diablo3_pose", assets, NORMAL_PASS)
+    except FileNotFoundError:
+        dia = None
+    lat = {}
+
+    def host_call_ms(sc, shader, w, h, shadow, reps=30):
+        objs = sc.upload(ctx)
+        u = hana.default_uniforms(w, h, shadow)
+        col = np.zeros((h, w, 4), np.uint8)
+        col[..., 3] = 1
+        dep = np.full((h, w), hana.FLT_MAX, np.float32)
+        ts = []
+        for i in range(reps + 3):
+            t0 = time.perf_counter()
+            ctx.draw_model_host(col, dep, objs[0], shader, u, objs[1], objs[2], assume_cleared=True)
+            ts.append((time.perf_counter() - t0) * 1e3)
+        for o in objs:
+            o.close()
+        ts = sorted(ts[3:])
+        return {"median": ts[len(ts) // 2], "min": ts[0], "p90": ts[int(len(ts) * 0.9)]}
+
+    if dia is not None:
+        F = 256
+        objs = dia.upload(ctx)
+        arr = hana.orbit_sweep_uniforms(1000, 600, 0, F, frames_per_turn=ORBIT)
+        sw = ctx.sweep(1000, 600, F)
+        for _ in range(2):
+            sw.render(objs[0], hana.NORMALMAP, arr, objs[1], objs[2])
+        ctx.sync()
+        ctx.timer_start()
+        for _ in range(5):
+            sw.render(objs[0], hana.NORMALMAP, arr, objs[1], objs[2])
+        ms = ctx.timer_stop() / 5
+        for o in (sw,) + tuple(objs):
+            o.close()
+        single = host_call_ms(dia, hana.NORMALMAP, 1000, 600, True)
+        out["readme_workload"] = {"config": "diablo3_pose, NormalMapShader + shadow, 1000x600 (README.md:5, main.cpp:7-8)",
+                                  "published_fps": 27, "published_on": "author's PC, incl. clear + present (README screenshot HUD)",
+                                  "frames_per_s_batched": F / (ms * 1e-3),
+                                  "single_frame_host_call_ms": single, "single_frame_fps": 1e3 / single["median"]}
+    af = hana.load_bundled(SCENE, assets, NORMAL_PASS)
+    lat["hana_draw_model_host_c1_800x600_blinn_noshadow"] = host_call_ms(af, hana.BLINN, 800, 600, False)
+    lat["hana_draw_model_host_c2_1920x1080_blinn_shadow"] = host_call_ms(af, hana.BLINN, 1920, 1080, True)
+    out["latency_ms"] = dict(lat, note="wall clock of ONE synchronous hana_draw_model_host call (Level-2 boundary, INTEGRATION.md): "
+                                       "uniform upload, both passes, colour + depth copied back to pageable host memory; the Level-1 "
+                                       "shim's record is profiles/r02_latency.json (tools/latency.py)")
+    return out
 
 
 if __name__ == "__main__":

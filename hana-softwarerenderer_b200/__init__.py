@@ -43,6 +43,7 @@ from .scene import (  # noqa: F401
     OrbitCamera,
     Scene,
     default_uniforms,
+    load_bundled,
     load_hscene,
     orbit_sweep_uniforms,
     scene_desc,

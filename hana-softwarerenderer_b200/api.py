@@ -99,6 +99,7 @@ def load():
         "hana_ctx_uses_tma": [vp],
         "hana_ctx_set_tma": [vp, i],
         "hana_ctx_sm_count": [vp],
+        "hana_ctx_wide_r8_launches": [vp, C.POINTER(C.c_uint64)],
         "hana_timer_start": [vp],
         "hana_timer_stop": [vp, C.POINTER(f)],
         "hana_ctx_profile": [vp, i],
@@ -131,6 +132,7 @@ def load():
         "hana_sweep_device_ptrs": [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(C.c_size_t)],
         "hana_sweep_checksums": [vp, i, vp],
         "hana_sweep_stats": [vp, i, vp],
+        "hana_sweep_overflow_count": [vp, C.POINTER(C.c_uint64)],
         "hana_sweep_present": [vp, i, i, i, vp, C.POINTER(vp)],
         "hana_sweep_set_bands": [vp, i, i, i, i],
         "hana_sweep_render_pass": [vp, i, vp, i, vp, i, vp, vp, vp, f],
@@ -210,6 +212,12 @@ class Context:
     @property
     def sm_count(self):
         return self.L.hana_ctx_sm_count(self.h)
+
+    @property
+    def wide_r8_launches(self):
+        n = C.c_uint64()
+        _ck(self.L.hana_ctx_wide_r8_launches(self.h, C.byref(n)))
+        return int(n.value)
 
     def timer_start(self):
         _ck(self.L.hana_timer_start(self.h))
@@ -462,6 +470,12 @@ class Sweep:
         out = np.zeros(n_frames, np.uint64)
         _ck(self.ctx.L.hana_sweep_checksums(self.h, n_frames, _ptr(out)))
         return out
+
+    def overflow_count(self):
+        """Batches that ran out of scratch and were overwritten before they could be rendered again (0 = none)."""
+        n = C.c_uint64()
+        _ck(self.ctx.L.hana_sweep_overflow_count(self.h, C.byref(n)))
+        return int(n.value)
 
     def stats(self, frame):
         s = HanaStats()

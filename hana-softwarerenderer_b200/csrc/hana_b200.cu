@@ -103,7 +103,9 @@ struct hana_ctx {
     hana_sweep* host_sweep = nullptr;
     hana_rb* host_frame = nullptr;
     hana_rb* host_shadow = nullptr;
-    int occ[HANA_SHADER_COUNT][3];
+    int occ[HANA_SHADER_COUNT][N_RASTER_MODES];
+    uint32_t r8_slot_limit = R8_SLOT_LIMIT; /* HANA_R8_SLOT_LIMIT in the environment lowers it (tests force the WIDE variant) */
+    uint64_t wide_r8_launches = 0;
 };
 
 struct hana_model {
@@ -146,10 +148,21 @@ struct hana_sweep {
     /* asynchronous rendering: a render is launched without any read-back; what it needed is checked (and the batch
      * re-rendered with larger scratch if something was dropped) at the sweep's next synchronisation point */
     OverflowRecord* overflow;      /* device */
+    /* A render that is superseded by the next one before anybody synchronised with it (back-to-back submissions) is
+     * not forgotten: its needs land in a slot of their own and are examined, without blocking, at later calls; a batch
+     * that ran out of scratch is counted (hana_sweep_overflow_count) and the scratch grows for the batches that follow. */
+    enum { CHECK_RING = 8, SLOT_PASSES_OK = CHECK_RING + 1, NEED_SLOTS = CHECK_RING + 2 };
     struct Pinned {
-        OverflowRecord need;
+        OverflowRecord need[NEED_SLOTS];
         PassCounters counters[2];
     }* pin;                        /* pinned host */
+    cudaEvent_t ev_check[CHECK_RING + 1];
+    struct Check {
+        int slot;
+        uint32_t tri_cap, pool_cap;
+    } checks[CHECK_RING];
+    int check_tail, n_checks, next_slot;
+    uint64_t overflow_batches;
     uint32_t* tri_counts_pin;      /* pinned host: [2][max_frames] */
     cudaEvent_t ev_render, ev_copy;
     bool copy_in_flight;
@@ -165,6 +178,7 @@ struct hana_sweep {
         uint8_t clear_rgba[4] = {0, 0, 0, 0};
         float clear_depth = 0.f;
         uint32_t tri_cap = 0, pool_cap = 0;
+        int slot = 0;
     } pending;
 };
 
@@ -237,6 +251,10 @@ extern "C" int hana_ctx_create(int device, hana_ctx** out) {
         ctx->encode = (EncodeTiledFn)fn;
     else
         cudaGetLastError();
+    if (const char* lim = getenv("HANA_R8_SLOT_LIMIT")) {
+        const long v = atol(lim);
+        if (v >= 0 && (unsigned long)v < R8_SLOT_LIMIT) ctx->r8_slot_limit = (uint32_t)v;
+    }
     const char* no_tma = getenv("HANA_NO_TMA");
     ctx->use_tma = ctx->encode != nullptr && !(no_tma && no_tma[0] == '1');
     CU_TRY(cudaMalloc(&ctx->u_raw, sizeof(HanaUniforms)));
@@ -290,10 +308,14 @@ extern "C" int hana_ctx_set_stream(hana_ctx* ctx, void* cuda_stream) {
     return HANA_OK;
 }
 static int sweep_verify(hana_sweep* s);
+static int sweep_poll_checks(hana_sweep* s, bool wait_all);
 extern "C" int hana_sync(hana_ctx* ctx) {
     if (!ctx) return fail(HANA_E_INVALID, "ctx is NULL");
     HANA_TRY(use_device(ctx));
-    for (hana_sweep* s : ctx->sweeps) HANA_TRY(sweep_verify(s)); /* re-renders a batch that ran out of scratch */
+    for (hana_sweep* s : ctx->sweeps) {
+        HANA_TRY(sweep_poll_checks(s, true));
+        HANA_TRY(sweep_verify(s)); /* re-renders a batch that ran out of scratch */
+    }
     CU_TRY(cudaStreamSynchronize(ctx->stream));
     CU_TRY(cudaStreamSynchronize(ctx->copy_stream));
     return HANA_OK;
@@ -310,6 +332,11 @@ extern "C" int hana_ctx_set_tma(hana_ctx* ctx, int enable) {
     return HANA_OK;
 }
 extern "C" int hana_ctx_sm_count(hana_ctx* ctx) { return ctx ? ctx->sm_count : 0; }
+extern "C" int hana_ctx_wide_r8_launches(hana_ctx* ctx, uint64_t* out) {
+    if (!ctx || !out) return fail(HANA_E_INVALID, "NULL argument");
+    *out = ctx->wide_r8_launches;
+    return HANA_OK;
+}
 
 /* ---- profiling (CUDA events around each kernel class, on the launching stream) ---- */
 static void prof_begin(hana_ctx* ctx, int kind, cudaEvent_t* a, cudaEvent_t* b, cudaStream_t st = nullptr) {
@@ -382,6 +409,7 @@ extern "C" int hana_timer_stop(hana_ctx* ctx, float* ms) {
     if (!ctx || !ms) return fail(HANA_E_INVALID, "NULL argument");
     HANA_TRY(use_device(ctx));
     for (hana_sweep* s : ctx->sweeps) { /* the timed region ends when checked frames (and their copies) are complete */
+        HANA_TRY(sweep_poll_checks(s, true));
         HANA_TRY(sweep_verify(s));
         if (s->copy_in_flight) CU_TRY(cudaStreamWaitEvent(ctx->stream, s->ev_copy, 0));
     }
@@ -465,8 +493,14 @@ extern "C" int hana_texture_upload(hana_ctx* ctx, const uint8_t* data, int w, in
         cudaGetLastError();
         return fail(HANA_E_CUDA, "cudaMalloc failed for the texture");
     }
-    CU_TRY(cudaMemcpyAsync(t->texels, tex.data(), n * 4, cudaMemcpyHostToDevice, ctx->stream));
-    CU_TRY(cudaStreamSynchronize(ctx->stream));
+    cudaError_t ce = cudaMemcpyAsync(t->texels, tex.data(), n * 4, cudaMemcpyHostToDevice, ctx->stream);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(ctx->stream);
+    if (ce != cudaSuccess) {
+        cudaFree(t->texels);
+        delete t;
+        cudaGetLastError();
+        return fail(HANA_E_CUDA, std::string("texture upload failed: ") + cudaGetErrorString(ce));
+    }
     *out = t;
     return HANA_OK;
 }
@@ -641,8 +675,12 @@ static int grow(T** ptr, size_t* cap, size_t need, hana_ctx* ctx) {
 template <int MODE>
 static int launch_raster(cudaStream_t st, int shader, int blocks, const RasterParams& rp, const CUtensorMap& a,
                          const CUtensorMap& b, const CUtensorMap& c) {
+    if constexpr (mode_is_r8(MODE)) { /* the 1-byte maps take the ShadowShader only */
+        raster_kernel<HANA_SHADER_SHADOW, MODE><<<blocks, RW_THREADS, 0, st>>>(rp, a, b, c);
+        return HANA_OK;
+    }
 #define HANA_RASTER_CASE(S) \
-    case S: raster_kernel<S, MODE><<<blocks, RW_THREADS, 0, st>>>(rp, a, b, c); break;
+    case S: if constexpr (!mode_is_r8(MODE)) raster_kernel<S, MODE><<<blocks, RW_THREADS, 0, st>>>(rp, a, b, c); break;
     switch (shader) {
         HANA_RASTER_CASE(HANA_SHADER_SHADOW)
         HANA_RASTER_CASE(HANA_SHADER_BLINN)
@@ -660,8 +698,12 @@ static int launch_raster(cudaStream_t st, int shader, int blocks, const RasterPa
 template <int MODE>
 static int raster_occupancy(int shader) {
     int occ = 0;
+    if constexpr (mode_is_r8(MODE)) {
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, raster_kernel<HANA_SHADER_SHADOW, MODE>, RW_THREADS, 0);
+        return occ;
+    }
 #define HANA_OCC_CASE(S) \
-    case S: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, raster_kernel<S, MODE>, RW_THREADS, 0); break;
+    case S: if constexpr (!mode_is_r8(MODE)) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, raster_kernel<S, MODE>, RW_THREADS, 0); break;
     switch (shader) {
         HANA_OCC_CASE(HANA_SHADER_SHADOW)
         HANA_OCC_CASE(HANA_SHADER_BLINN)
@@ -677,7 +719,7 @@ static int raster_occupancy(int shader) {
 
 static int run_pass(hana_ctx* ctx, const PassDesc& d) {
     if (d.shader < 0 || d.shader >= HANA_SHADER_COUNT) return fail(HANA_E_UNSUPPORTED, "unknown shader id");
-    if (d.mode == MODE_SHADOW_R8 && d.shader != HANA_SHADER_SHADOW)
+    if (mode_is_r8(d.mode) && d.shader != HANA_SHADER_SHADOW)
         return fail(HANA_E_INVALID, "R8 targets take the ShadowShader only");
     const int tiles_x = (d.W + TILE - 1) / TILE, tiles_y = (d.H + TILE - 1) / TILE;
     const size_t n_tiles = (size_t)tiles_x * tiles_y;
@@ -864,11 +906,15 @@ static int run_pass(hana_ctx* ctx, const PassDesc& d) {
     rp.primid = d.primid;
     rp.pixels_covered = d.pixels_covered;
 
-    int& occ = ctx->occ[d.shader][d.mode];
+    /* MODE_SHADOW_R8 packs {shadow byte << 24 | triangle slot}: a pass that may emit more triangles per frame than 24 bits
+     * address takes the WIDE variant (hana_kernels.cuh; ctx->r8_slot_limit is R8_SLOT_LIMIT unless a test lowered it) */
+    const int mode = (d.mode == MODE_SHADOW_R8 && p.tri_cap > ctx->r8_slot_limit) ? (int)MODE_SHADOW_R8_WIDE : d.mode;
+    int& occ = ctx->occ[d.shader][mode];
     if (occ == 0) {
-        occ = d.mode == MODE_CLEAR_FOLD ? raster_occupancy<MODE_CLEAR_FOLD>(d.shader)
-              : d.mode == MODE_RMW      ? raster_occupancy<MODE_RMW>(d.shader)
-                                        : raster_occupancy<MODE_SHADOW_R8>(HANA_SHADER_SHADOW);
+        occ = mode == MODE_CLEAR_FOLD  ? raster_occupancy<MODE_CLEAR_FOLD>(d.shader)
+              : mode == MODE_RMW       ? raster_occupancy<MODE_RMW>(d.shader)
+              : mode == MODE_SHADOW_R8 ? raster_occupancy<MODE_SHADOW_R8>(HANA_SHADER_SHADOW)
+                                       : raster_occupancy<MODE_SHADOW_R8_WIDE>(HANA_SHADER_SHADOW);
         cudaGetLastError();
         if (occ <= 0) occ = 1;
     }
@@ -880,9 +926,11 @@ static int run_pass(hana_ctx* ctx, const PassDesc& d) {
     const CUtensorMap& tb = d.tm_depth ? *d.tm_depth : dummy;
     const CUtensorMap& tc = d.tm_r8 ? *d.tm_r8 : dummy;
     prof_begin(ctx, d.prof_kind, &ea, &eb, st);
-    int r = d.mode == MODE_CLEAR_FOLD ? launch_raster<MODE_CLEAR_FOLD>(st, d.shader, blocks, rp, ta, tb, tc)
-            : d.mode == MODE_RMW      ? launch_raster<MODE_RMW>(st, d.shader, blocks, rp, ta, tb, tc)
-                                      : launch_raster<MODE_SHADOW_R8>(st, HANA_SHADER_SHADOW, blocks, rp, ta, tb, tc);
+    int r = mode == MODE_CLEAR_FOLD  ? launch_raster<MODE_CLEAR_FOLD>(st, d.shader, blocks, rp, ta, tb, tc)
+            : mode == MODE_RMW       ? launch_raster<MODE_RMW>(st, d.shader, blocks, rp, ta, tb, tc)
+            : mode == MODE_SHADOW_R8 ? launch_raster<MODE_SHADOW_R8>(st, HANA_SHADER_SHADOW, blocks, rp, ta, tb, tc)
+                                     : launch_raster<MODE_SHADOW_R8_WIDE>(st, HANA_SHADER_SHADOW, blocks, rp, ta, tb, tc);
+    if (mode == MODE_SHADOW_R8_WIDE) ctx->wide_r8_launches++;
     prof_end(ctx, d.prof_kind, ea, eb, st);
     HANA_TRY(r);
     ctx->launches++;
@@ -1048,6 +1096,9 @@ extern "C" int hana_sweep_create(hana_ctx* ctx, int width, int height, int max_f
     s->color = nullptr; s->depth = nullptr; s->shadow_r8 = nullptr; s->u_raw = nullptr; s->u_dev = nullptr;
     s->checksums = nullptr; s->pix_counts = nullptr; s->overflow = nullptr; s->pin = nullptr; s->tri_counts_pin = nullptr;
     s->ev_render = nullptr; s->ev_copy = nullptr; s->copy_in_flight = false; s->present_buf = nullptr; s->present_cap = 0;
+    for (auto& e : s->ev_check) e = nullptr;
+    s->check_tail = s->n_checks = s->next_slot = 0;
+    s->overflow_batches = 0;
     cudaError_t e = cudaMalloc(&s->color, n * 4 * max_frames);
     if (e == cudaSuccess) e = cudaMalloc(&s->depth, n * 4 * max_frames);
     if (e == cudaSuccess) e = cudaMalloc(&s->shadow_r8, s->shadow_frame_bytes * max_frames);
@@ -1060,6 +1111,8 @@ extern "C" int hana_sweep_create(hana_ctx* ctx, int width, int height, int max_f
     if (e == cudaSuccess) e = cudaMallocHost(&s->tri_counts_pin, sizeof(uint32_t) * 2 * max_frames);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev_render, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev_copy, cudaEventDisableTiming);
+    for (auto& ev : s->ev_check)
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
     if (e != cudaSuccess) {
         cudaGetLastError();
         hana_sweep_destroy(s);
@@ -1092,6 +1145,8 @@ extern "C" int hana_sweep_destroy(hana_sweep* s) {
     if (s->tri_counts_pin) cudaFreeHost(s->tri_counts_pin);
     if (s->ev_render) cudaEventDestroy(s->ev_render);
     if (s->ev_copy) cudaEventDestroy(s->ev_copy);
+    for (auto ev : s->ev_check)
+        if (ev) cudaEventDestroy(ev);
     if (ctx->host_sweep == s) ctx->host_sweep = nullptr;
     ctx->sweeps.erase(std::remove(ctx->sweeps.begin(), ctx->sweeps.end(), s), ctx->sweeps.end());
     delete s;
@@ -1212,15 +1267,48 @@ static int sweep_render_passes(hana_sweep* s, const hana_model* model, int shade
     return HANA_OK;
 }
 
+static int grow_scratch_for(hana_ctx* ctx, const OverflowRecord& need) {
+    ctx->tri_cap_hint = std::max(ctx->tri_cap_hint, need.tri_needed + need.tri_needed / 8 + 64);
+    for (Scratch* sp : {&ctx->sc, &ctx->sc2}) /* headroom for the other frames of an orbit */
+        if ((size_t)need.pool_needed > sp->pool_cap / 4 && (sp == &ctx->sc || sp->tile_recs))
+            HANA_TRY(grow(&sp->tile_recs, &sp->pool_cap, ((size_t)need.pool_needed + need.pool_needed / 4) * 4, ctx));
+    return HANA_OK;
+}
+
+/* Renders that were superseded before anybody synchronised with them: examine those that have completed (all of them
+ * if wait_all). Their frames are gone, so a batch that ran out of scratch cannot be rendered again; it is counted and
+ * the scratch is grown so that the batches that follow fit. */
+static int sweep_poll_checks(hana_sweep* s, bool wait_all) {
+    while (s->n_checks > 0) {
+        const hana_sweep::Check c = s->checks[s->check_tail];
+        if (wait_all) {
+            CU_TRY(cudaEventSynchronize(s->ev_check[c.slot]));
+        } else {
+            const cudaError_t q = cudaEventQuery(s->ev_check[c.slot]);
+            if (q == cudaErrorNotReady) break;
+            CU_TRY(q);
+        }
+        s->check_tail = (s->check_tail + 1) % hana_sweep::CHECK_RING;
+        s->n_checks--;
+        const OverflowRecord need = s->pin->need[c.slot];
+        if (need.tri_needed > c.tri_cap || need.pool_needed > c.pool_cap) {
+            s->overflow_batches++;
+            HANA_TRY(grow_scratch_for(s->ctx, need));
+        }
+    }
+    return HANA_OK;
+}
+
 /* The sweep's synchronisation point: waits for its last render, and if that render ran out of scratch (triangles
  * or tile-list records were dropped), grows the scratch and renders the batch again, this time with read-backs. */
 static int sweep_verify(hana_sweep* s) {
     hana_ctx* ctx = s->ctx;
+    HANA_TRY(sweep_poll_checks(s, false));
     if (!s->pending.active) return HANA_OK;
-    CU_TRY(cudaEventSynchronize(s->ev_render));
     hana_sweep::Pending pd = s->pending;
+    CU_TRY(cudaEventSynchronize(s->ev_check[pd.slot]));
     s->pending.active = false;
-    const OverflowRecord need = s->pin->need;
+    const OverflowRecord need = s->pin->need[pd.slot];
     for (int pass = 0; pass < 2; pass++) {
         s->last_tri_counts[pass].assign(s->tri_counts_pin + (size_t)pass * s->max_frames,
                                         s->tri_counts_pin + (size_t)pass * s->max_frames + pd.n_frames);
@@ -1228,10 +1316,7 @@ static int sweep_verify(hana_sweep* s) {
     s->last_stats.tile_refs = s->pin->counters[1].pool_used;
     s->last_stats.tiles_touched = s->pin->counters[1].tiles_touched;
     if (need.tri_needed <= pd.tri_cap && need.pool_needed <= pd.pool_cap) return HANA_OK;
-    ctx->tri_cap_hint = std::max(ctx->tri_cap_hint, need.tri_needed + need.tri_needed / 8 + 64);
-    for (Scratch* sp : {&ctx->sc, &ctx->sc2}) /* headroom for the other frames of an orbit */
-        if ((size_t)need.pool_needed > sp->pool_cap / 4 && (sp == &ctx->sc || sp->tile_recs))
-            HANA_TRY(grow(&sp->tile_recs, &sp->pool_cap, ((size_t)need.pool_needed + need.pool_needed / 4) * 4, ctx));
+    HANA_TRY(grow_scratch_for(ctx, need));
     return sweep_render_passes(s, pd.model, pd.shader, pd.enable_shadow, pd.n_frames, pd.diffuse, pd.normal, pd.clear_rgba,
                                pd.clear_depth, false);
 }
@@ -1240,8 +1325,22 @@ static int sweep_render_common(hana_sweep* s, const hana_model* model, int shade
                                int enable_shadow, int n_frames, const hana_texture* diffuse, const hana_texture* normal,
                                const uint8_t clear_rgba[4], float clear_depth) {
     hana_ctx* ctx = s->ctx;
-    /* the previous render's frames are about to be overwritten: nothing to verify, but its copies must be out */
-    s->pending.active = false;
+    /* the previous render's frames are about to be overwritten: it cannot be rendered again, but what it needed is
+     * still examined once it has completed (sweep_poll_checks); its copies must be out */
+    if (s->pending.active) {
+        if (s->n_checks == hana_sweep::CHECK_RING) { /* ring full: wait for the oldest */
+            CU_TRY(cudaEventSynchronize(s->ev_check[s->checks[s->check_tail].slot]));
+        }
+        HANA_TRY(sweep_poll_checks(s, false));
+        hana_sweep::Check& c = s->checks[(s->check_tail + s->n_checks) % hana_sweep::CHECK_RING];
+        c.slot = s->pending.slot;
+        c.tri_cap = s->pending.tri_cap;
+        c.pool_cap = s->pending.pool_cap;
+        s->n_checks++;
+        s->pending.active = false;
+    } else {
+        HANA_TRY(sweep_poll_checks(s, false));
+    }
     if (s->copy_in_flight) {
         CU_TRY(cudaStreamWaitEvent(ctx->stream, s->ev_copy, 0));
         s->copy_in_flight = false;
@@ -1249,10 +1348,14 @@ static int sweep_render_common(hana_sweep* s, const hana_model* model, int shade
     HANA_TRY(upload_uniforms(ctx, host_uniforms, n_frames, s->u_raw, s->u_dev));
     CU_TRY(cudaMemsetAsync(s->overflow, 0, sizeof(OverflowRecord), ctx->stream));
     HANA_TRY(sweep_render_passes(s, model, shader_id, enable_shadow, n_frames, diffuse, normal, clear_rgba, clear_depth, true));
-    CU_TRY(cudaMemcpyAsync(&s->pin->need, s->overflow, sizeof(OverflowRecord), cudaMemcpyDeviceToHost, ctx->stream));
+    const int slot = s->next_slot;
+    s->next_slot = (slot + 1) % (hana_sweep::CHECK_RING + 1);
+    CU_TRY(cudaMemcpyAsync(&s->pin->need[slot], s->overflow, sizeof(OverflowRecord), cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(cudaEventRecord(s->ev_check[slot], ctx->stream));
     CU_TRY(cudaEventRecord(s->ev_render, ctx->stream));
     hana_sweep::Pending& pd = s->pending;
     pd.active = true;
+    pd.slot = slot;
     pd.model = model;
     pd.shader = shader_id;
     pd.enable_shadow = enable_shadow;
@@ -1377,16 +1480,24 @@ extern "C" int hana_sweep_passes_ok(hana_sweep* s, int* ok) {
     if (!s || !ok) return fail(HANA_E_INVALID, "NULL argument");
     hana_ctx* ctx = s->ctx;
     HANA_TRY(use_device(ctx));
-    CU_TRY(cudaMemcpyAsync(&s->pin->need, s->overflow, sizeof(OverflowRecord), cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(cudaMemcpyAsync(&s->pin->need[hana_sweep::SLOT_PASSES_OK], s->overflow, sizeof(OverflowRecord), cudaMemcpyDeviceToHost,
+                           ctx->stream));
     CU_TRY(cudaStreamSynchronize(ctx->stream));
-    const OverflowRecord need = s->pin->need;
+    const OverflowRecord need = s->pin->need[hana_sweep::SLOT_PASSES_OK];
     *ok = (need.tri_needed <= s->pending.tri_cap && need.pool_needed <= s->pending.pool_cap) ? 1 : 0;
-    if (!*ok) {
-        ctx->tri_cap_hint = std::max(ctx->tri_cap_hint, need.tri_needed + need.tri_needed / 8 + 64);
-        for (Scratch* sp : {&ctx->sc, &ctx->sc2})
-            if ((size_t)need.pool_needed > sp->pool_cap / 4 && (sp == &ctx->sc || sp->tile_recs))
-                HANA_TRY(grow(&sp->tile_recs, &sp->pool_cap, ((size_t)need.pool_needed + need.pool_needed / 4) * 4, ctx));
-    }
+    if (!*ok) HANA_TRY(grow_scratch_for(ctx, need));
+    return HANA_OK;
+}
+
+/* Batches of this sweep that ran out of triangle or tile-list scratch AND were overwritten by a later submission before
+ * they could be rendered again (only possible when renders are queued back to back without any synchronising call in
+ * between). Waits for every render queued so far. 0 = every frame handed out so far was complete. */
+extern "C" int hana_sweep_overflow_count(hana_sweep* s, uint64_t* out) {
+    if (!s || !out) return fail(HANA_E_INVALID, "NULL argument");
+    HANA_TRY(use_device(s->ctx));
+    HANA_TRY(sweep_poll_checks(s, true));
+    HANA_TRY(sweep_verify(s));
+    *out = s->overflow_batches;
     return HANA_OK;
 }
 

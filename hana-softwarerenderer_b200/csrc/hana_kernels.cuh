@@ -44,8 +44,13 @@ constexpr int SCAN_THREADS = 1024;
 enum RasterMode {
     MODE_CLEAR_FOLD = 0, /* target holds (clear colour, clear depth) before the draw; every tile is written once */
     MODE_RMW = 1,        /* target has contents that take part in the depth test; only covered pixels change */
-    MODE_SHADOW_R8 = 2   /* ShadowShader into the sweep's internal 1-byte-per-texel maps, cleared to 0 */
+    MODE_SHADOW_R8 = 2,  /* ShadowShader into the sweep's internal 1-byte-per-texel maps, cleared to 0 */
+    MODE_SHADOW_R8_WIDE = 3 /* the same for passes that may emit more than R8_SLOT_LIMIT triangles per frame: the shadow byte lives
+                               beside the state word instead of in its top 8 bits, so the triangle slot keeps all 32 bits */
 };
+constexpr int N_RASTER_MODES = 4;
+constexpr uint32_t R8_SLOT_LIMIT = 0x00FFFFFEu; /* largest triangle capacity MODE_SHADOW_R8's 24-bit slot field can address */
+__host__ __device__ constexpr bool mode_is_r8(int mode) { return mode == MODE_SHADOW_R8 || mode == MODE_SHADOW_R8_WIDE; }
 
 /* Device-side bookkeeping of one pass (all frames of a batch). */
 struct PassCounters {
@@ -537,15 +542,15 @@ constexpr uint32_t ORD_NONE = 0xFFFFFFFFu;
 template <int MODE>
 struct alignas(128) WarpTile {
     /* TMA sources/destinations first: each 128-byte aligned */
-    uint32_t color[MODE == MODE_SHADOW_R8 ? 32 : TILE_PIX]; /* box 16x16 u32; CLEAR_FOLD: holds the parked w0 of a pixel until it is shaded */
-    float depth[MODE == MODE_SHADOW_R8 ? 32 : TILE_PIX];
-    uint8_t r8[MODE == MODE_SHADOW_R8 ? TILE_PIX : 128];    /* box 16x16 u8 */
-    uint32_t ord[MODE == MODE_SHADOW_R8 ? 32 : TILE_PIX];   /* winning triangle slot per pixel, parked for shading */
-    float pw1[MODE == MODE_SHADOW_R8 ? 32 : TILE_PIX];      /* parked weights of the winning fragment */
-    float pw2[MODE == MODE_SHADOW_R8 ? 32 : TILE_PIX];
+    uint32_t color[mode_is_r8(MODE) ? 32 : TILE_PIX]; /* box 16x16 u32; CLEAR_FOLD: holds the parked w0 of a pixel until it is shaded */
+    float depth[mode_is_r8(MODE) ? 32 : TILE_PIX];
+    uint8_t r8[mode_is_r8(MODE) ? TILE_PIX : 128];    /* box 16x16 u8 */
+    uint32_t ord[mode_is_r8(MODE) ? 32 : TILE_PIX];   /* winning triangle slot per pixel, parked for shading */
+    float pw1[mode_is_r8(MODE) ? 32 : TILE_PIX];      /* parked weights of the winning fragment */
+    float pw2[mode_is_r8(MODE) ? 32 : TILE_PIX];
     float pw0_own[MODE == MODE_RMW ? TILE_PIX : 32];        /* RMW: color[] holds the target's pixels */
     float4 tri[RW_CHUNK * RW_REC_Q];                        /* staged raster records */
-    float4 sattr[MODE == MODE_SHADOW_R8 ? RW_CHUNK * 2 : 1]; /* SHADOW_R8: their (1/w, clip z) blocks */
+    float4 sattr[mode_is_r8(MODE) ? RW_CHUNK * 2 : 1]; /* SHADOW_R8: their (1/w, clip z) blocks */
     FragUniforms fu;                                        /* the tile's frame: what fragment() reads */
     alignas(8) uint64_t bar;
 };
@@ -569,7 +574,7 @@ __device__ __forceinline__ void clear_slots(const RasterParams& q, RasterSmem<MO
     const int tx = t % p.tiles_x, ty = t / p.tiles_x;
     if (s < n_slots && ty >= p.band_y0 && ty < p.band_y1 && p.tile_count[(size_t)f * p.tile_pad + tile_slot(p, t)] == 0u) {
         if (q.use_tma) {
-            if (MODE == MODE_SHADOW_R8) {
+            if (mode_is_r8(MODE)) {
                 tma_store_3d(&tm_r8, sm.clr_r8, tx * TILE, ty * TILE, f);
             } else {
                 tma_store_3d(&tm_color, sm.clr_color, tx * TILE, ty * TILE, f);
@@ -583,7 +588,7 @@ __device__ __forceinline__ void clear_slots(const RasterParams& q, RasterSmem<MO
                 for (int xx = 0; xx < TILE; xx++) {
                     const int px = tx * TILE + xx;
                     if (px >= p.W) break;
-                    if (MODE == MODE_SHADOW_R8) {
+                    if (mode_is_r8(MODE)) {
                         q.shadow_out[(size_t)f * q.shadow_out_frame_stride + (size_t)py * q.shadow_out_pitch + px] = 0;
                     } else {
                         const size_t o = (size_t)f * q.frame_stride + (size_t)py * p.W + px;
@@ -594,6 +599,12 @@ __device__ __forceinline__ void clear_slots(const RasterParams& q, RasterSmem<MO
             }
         }
     }
+}
+
+/* word with byte K replaced by the low byte of b (one PRMT) */
+template <int K>
+__device__ __forceinline__ uint32_t put_byte(uint32_t word, uint32_t b) {
+    return __byte_perm(word, b, K == 0 ? 0x3214 : (K == 1 ? 0x3240 : (K == 2 ? 0x3410 : 0x4210)));
 }
 
 /* atomicAdd whose result is NOT needed yet. nvcc turns an atomicAdd under `if (lane == 0)` into its warp-aggregated
@@ -683,9 +694,13 @@ __global__ void __launch_bounds__(RW_THREADS, ShaderAttrs<SHADER>::LIT ? HANA_OC
     constexpr int NQ = ShaderAttrs<SHADER>::NQ;
     constexpr unsigned FULL = 0xFFFFFFFFu;
     /* SHADOW_R8 (always the ShadowShader): its one-attribute fragment() is evaluated right where a fragment wins the
-     * resolve and the byte rides in the top 8 bits of the state word, so nothing is parked or re-fetched afterwards */
-    constexpr bool INLOOP = (MODE == MODE_SHADOW_R8);
-    constexpr uint32_t SLOT_MASK = INLOOP ? 0x00FFFFFFu : 0xFFFFFFFFu;
+     * resolve, so nothing is parked or re-fetched afterwards. The byte rides in the top 8 bits of the state word, which
+     * leaves 24 bits for the triangle slot: run_pass routes a pass whose per-frame triangle capacity exceeds
+     * R8_SLOT_LIMIT to the WIDE variant, which keeps the eight bytes of a lane packed in two registers of their own
+     * (replaced with one PRMT per win) and the slot at 32 bits — two more registers, ~3 % slower, no limit. */
+    constexpr bool INLOOP = mode_is_r8(MODE);
+    constexpr bool WIDE = (MODE == MODE_SHADOW_R8_WIDE);
+    constexpr uint32_t SLOT_MASK = (INLOOP && !WIDE) ? 0x00FFFFFFu : 0xFFFFFFFFu;
     __shared__ RasterSmem<MODE> sm;
     const PassParams& p = q.p;
     const unsigned lane = threadIdx.x & 31u, wid = __shfl_sync(FULL, threadIdx.x >> 5, 0); /* the broadcast lets ptxas keep the warp's shared-memory base in a uniform register instead of rebuilding it from S2R in the record loop */
@@ -757,6 +772,7 @@ __global__ void __launch_bounds__(RW_THREADS, ShaderAttrs<SHADER>::LIT ? HANA_OC
 
         float bz[8];
         uint32_t bj[8];
+        uint32_t bb[2] = {0u, 0u}; /* WIDE: the ShadowShader byte of sub-block sb in byte sb & 3 of bb[sb >> 2]; 0 where nothing was drawn */
 #pragma unroll
         for (int sb = 0; sb < 8; sb++) {
             bz[sb] = q.clear_depth;
@@ -889,8 +905,13 @@ __global__ void __launch_bounds__(RW_THREADS, ShaderAttrs<SHADER>::LIT ? HANA_OC
                                     const f2 SUM = f2_add(f2_add(V0, V1), V2);
                                     const f2 NORM = f2_rcp(SUM);
                                     const f2 AT = f2_mul(f2_add(f2_add(f2_mul(f2_dup(a.x), V0), f2_mul(f2_dup(a.y), V1)), f2_mul(f2_dup(a.z), V2)), NORM);
-                                    if (winA) bj[ia] |= shadow_byte(f2_lo(AT)) << 24;
-                                    if (winB) bj[ib] |= shadow_byte(f2_hi(AT)) << 24;
+                                    if (WIDE) {
+                                        if (winA) bb[ia >> 2] = put_byte<ia & 3>(bb[ia >> 2], shadow_byte(f2_lo(AT)));
+                                        if (winB) bb[ib >> 2] = put_byte<ib & 3>(bb[ib >> 2], shadow_byte(f2_hi(AT)));
+                                    } else {
+                                        if (winA) bj[ia] |= shadow_byte(f2_lo(AT)) << 24;
+                                        if (winB) bj[ib] |= shadow_byte(f2_hi(AT)) << 24;
+                                    }
                                 }
                             } else {
                                 if (winA) {
@@ -938,7 +959,7 @@ __global__ void __launch_bounds__(RW_THREADS, ShaderAttrs<SHADER>::LIT ? HANA_OC
             }
         }
 
-        if (tma && MODE == MODE_SHADOW_R8) {
+        if (tma && mode_is_r8(MODE)) {
             if (lane == 0) tma_wait_read0(); /* the previous tile's store has drained the staging tile */
             __syncwarp();
         }
@@ -947,7 +968,7 @@ __global__ void __launch_bounds__(RW_THREADS, ShaderAttrs<SHADER>::LIT ? HANA_OC
 #pragma unroll
             for (int sb = 0; sb < 8; sb++) {
                 const int pix = pix0 + (sb >> 1) * 64 + (sb & 1) * 8;
-                const uint8_t v = (uint8_t)(bj[sb] == ORD_NONE ? 0u : (bj[sb] >> 24));
+                const uint8_t v = WIDE ? (uint8_t)(bb[sb >> 2] >> (8 * (sb & 3))) : (uint8_t)(bj[sb] == ORD_NONE ? 0u : (bj[sb] >> 24));
                 if (q.pixels_covered) covered_acc += __popc(__ballot_sync(FULL, bj[sb] != ORD_NONE));
                 if (tma) {
                     wt.r8[pix] = v;
@@ -1003,7 +1024,7 @@ __global__ void __launch_bounds__(RW_THREADS, ShaderAttrs<SHADER>::LIT ? HANA_OC
             fence_async_smem();
             __syncwarp();
             if (lane == 0) {
-                if (MODE == MODE_SHADOW_R8) {
+                if (mode_is_r8(MODE)) {
                     tma_store_3d(&tm_r8, wt.r8, X0, Y0, f);
                 } else {
                     tma_store_3d(&tm_color, wt.color, X0, Y0, f);

@@ -109,6 +109,26 @@ class Scene:
         return ctx.model(self.a2v), ctx.texture(self.diffuse), ctx.texture(self.normal)
 
 
+ASSET_ROOT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "assets")
+
+
+def load_bundled(name, root=None, normal_pass=1):
+    """A scene of the reference's assets/ layout (<root>/<name>/<name>.obj, <name>_diffuse.tga, <name>_nm_tangent.tga:
+    model.cpp:6-48), read by THIS library's own OBJ / TGA readers (hana_obj_load, hana_tga_load). Raises if the files
+    are not there: nothing is substituted."""
+    from .api import obj_load, tga_load
+    d = os.path.join(root or ASSET_ROOT, name)
+    obj = os.path.join(d, name + ".obj")
+    if not os.path.exists(obj):
+        raise FileNotFoundError("bundled scene %s not found under %s (__graft_entry__.build() copies the reference's "
+                                "assets/ there)" % (name, root or ASSET_ROOT))
+    tex = []
+    for suffix in ("_diffuse.tga", "_nm_tangent.tga"):
+        p = os.path.join(d, name + suffix)
+        tex.append(tga_load(p, model_flip=True) if os.path.exists(p) else None)
+    return Scene(name, obj_load(obj, normal_pass), tex[0], tex[1])
+
+
 def load_hscene(path):
     """A packed scene: npz with a2v, diffuse, normal (written by oracle/pack_assets.py from the bundled assets)."""
     z = np.load(path)

@@ -115,6 +115,10 @@ HANA_API int hana_ctx_launch_count(hana_ctx* ctx, uint64_t* out);
 HANA_API int hana_ctx_uses_tma(hana_ctx* ctx);
 HANA_API int hana_ctx_set_tma(hana_ctx* ctx, int enable);
 HANA_API int hana_ctx_sm_count(hana_ctx* ctx);
+/* Shadow-map passes that took the wide-slot rasteriser (a pass whose per-frame triangle capacity exceeds what the
+ * 24-bit slot field of the packed {shadow byte, triangle slot} state addresses; HANA_R8_SLOT_LIMIT in the environment
+ * lowers the threshold so that tests can force the path). */
+HANA_API int hana_ctx_wide_r8_launches(hana_ctx* ctx, uint64_t* out);
 
 /* --- measurement ------------------------------------------------------------ */
 /* CUDA-event timing on the context's stream. hana_timer_stop synchronises. */
@@ -247,6 +251,10 @@ HANA_API int hana_sweep_device_ptrs(hana_sweep* s, void** color_dev, void** dept
  * last batch, computed on the device; used by the multi-GPU sharding tests. */
 HANA_API int hana_sweep_checksums(hana_sweep* s, int n_frames, uint64_t* out_host);
 HANA_API int hana_sweep_stats(hana_sweep* s, int frame, HanaStats* out); /* synchronises */
+/* Batches of this sweep that ran out of internal scratch AND were overwritten by a later submission before a
+ * synchronising call could render them again (only possible when renders are queued back to back, as a throughput
+ * loop does). Waits for everything queued so far. 0 = no frame handed out so far was incomplete. */
+HANA_API int hana_sweep_overflow_count(hana_sweep* s, uint64_t* out);
 
 /* --- one frame split by screen tiles over several GPUs (BASELINE.json north_star, optional mode) --
  * The frame's 16x16 tiles are dealt to the GPUs in bands of tile rows. Geometry is replicated; each GPU rasterises

@@ -3,9 +3,14 @@
 issue utilisation, occupancy, registers. The source of the tables under profiles/.
 
   python tools/ncu_summary.py gpurun_out/prof_all.ncu-rep > profiles/rNN_step_kernels.md
+  python tools/ncu_summary.py gpurun_out/prof_all.ncu-rep --traffic 256 profiles/raster_main_dram.json
+      also writes the DRAM traffic (read + write) of the raster_main launch, per frame (the capture rendered 256 frames
+      per launch), to the file bench.py reads `roofline.traffic` from
 """
 import csv
 import io
+import json
+import os
 import subprocess
 import sys
 
@@ -47,6 +52,24 @@ def main():
             u = units[i]
             cells.append(v + ((" " + u) if u and u not in ("%", "inst", "register/thread", "") else ""))
         print("| %d | `%s` | %s |" % (k, r[name_i].split("(")[0][:48], " | ".join(cells)))
+
+
+    if "--traffic" in sys.argv:
+        k = sys.argv.index("--traffic")
+        frames, dst = int(sys.argv[k + 1]), sys.argv[k + 2]
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+        ri, wi = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+        best = None
+        for r in data:
+            if "raster_kernel<(int)1, (int)0>" in r[name_i]:
+                best = r  # the last such launch (steady state)
+        if best is None:
+            raise SystemExit("no raster_kernel<BLINN, CLEAR_FOLD> launch in the report")
+        rd, wr = float(best[ri]) * scale[units[ri]], float(best[wi]) * scale[units[wi]]
+        json.dump({"kernel": "raster_kernel<BLINN, CLEAR_FOLD>", "dram_read_bytes_per_launch": rd, "dram_write_bytes_per_launch": wr,
+                   "frames_per_launch": frames, "bytes_per_frame": (rd + wr) / frames,
+                   "source": "ncu --set full capture %s (dram__bytes_read.sum + dram__bytes_write.sum of one launch of %d frames)" %
+                             (os.path.basename(rep), frames)}, open(dst, "w"), indent=1)
 
 
 if __name__ == "__main__":
