@@ -632,20 +632,20 @@ __device__ __forceinline__ uint32_t subblock_mask(int x0, int x1, int y0, int y1
     return cm * spread;
 }
 
-/* graphics.cpp:362-370 for one fragment: interpolate the attributes the shader reads, run fragment(). The fragment
- * stage's uniforms arrive as 11 128-bit loads. FAST: sqrt/reciprocal fast paths with one shared range check (qsqrt). */
+/* graphics.cpp:362-373 for one fragment: interpolate the attributes the shader reads, run fragment(), return the R,G,B
+ * bytes set_color stores (renderbuffer.cpp:38-44). The fragment stage's uniforms arrive as 128-bit loads. FAST: sqrt /
+ * reciprocal fast paths with one shared range check (qsqrt); *bad tells the caller that an operand left their range. */
 template <int SHADER, bool FAST>
-__device__ __forceinline__ bool shade_fragment_t(const FragUniforms& fu, const float4* ap, float w0, float w1, float w2,
-                                                 const DevTexture& diffuse, const DevTexture& normal, const DevShadow& sh,
-                                                 float rgb[3]) {
+__device__ __forceinline__ uint32_t shade_fragment_t(const FragUniforms& fu, const float4* ap, float w0, float w1, float w2,
+                                                     const DevTexture& diffuse, const DevTexture& normal, const DevShadow& sh,
+                                                     bool& bad) {
     constexpr int NA = ShaderAttrs<SHADER>::NA;
     constexpr int NQ = ShaderAttrs<SHADER>::NQ;
-    bool bad = false;
+    bad = false;
     bool* pb = FAST ? &bad : nullptr;
     if (ShaderAttrs<SHADER>::LIT) {
         const LitAttrs la = interp_lit_packed(ap, w0, w1, w2, pb);
-        fragment_lit_packed<SHADER>(fu, la, diffuse, normal, sh, ap, rgb, pb);
-        return bad;
+        return fragment_lit_packed<SHADER>(fu, la, diffuse, normal, sh, ap, pb);
     }
     const float4 rw = __ldg(ap);
     VaryingWeights vw = varying_weights(w0, w1, w2, rw.x, rw.y, rw.z, pb);
@@ -661,30 +661,27 @@ __device__ __forceinline__ bool shade_fragment_t(const FragUniforms& fu, const f
     float attr[NA];
 #pragma unroll
     for (int k = 0; k < NA; k++) attr[k] = interp(vw, a[3 * k], a[3 * k + 1], a[3 * k + 2]);
+    float rgb[3];
     fragment_shader<SHADER>(fu, attr, diffuse, normal, sh, rgb, pb);
-    return bad;
+    return colour_bytes(rgb);
 }
-/* The rare re-evaluation with the full sqrt / reciprocal functions. Returns the colour bytes (by value: an rgb[] passed by
- * address into a non-inlined call would live in local memory in the caller's hot loop). */
+/* The rare re-evaluation with the full sqrt / reciprocal functions. */
 template <int SHADER>
 __device__ __noinline__ uint32_t shade_fragment_exact(const FragUniforms* fu, const float4* ap, float w0, float w1, float w2,
                                                       const DevTexture* diffuse, const DevTexture* normal, const DevShadow* sh) {
-    float c[3];
-    shade_fragment_t<SHADER, false>(*fu, ap, w0, w1, w2, *diffuse, *normal, *sh, c);
-    return colour_bytes(c);
+    bool bad;
+    return shade_fragment_t<SHADER, false>(*fu, ap, w0, w1, w2, *diffuse, *normal, *sh, bad);
 }
-/* graphics.cpp:362-373 for one fragment: the R,G,B bytes set_color stores (renderbuffer.cpp:38-44) */
 template <int SHADER>
 __device__ __forceinline__ uint32_t shade_fragment(const FragUniforms& fu, const float4* ap, float w0, float w1, float w2,
                                                    const DevTexture& diffuse, const DevTexture& normal, const DevShadow& sh) {
-    float rgb[3];
-    if (ShaderAttrs<SHADER>::LIT) { /* ten sqrt/reciprocal sites: worth the shared range check */
-        if (shade_fragment_t<SHADER, true>(fu, ap, w0, w1, w2, diffuse, normal, sh, rgb)) /* an operand left the fast paths' range */
-            return shade_fragment_exact<SHADER>(&fu, ap, w0, w1, w2, &diffuse, &normal, &sh);
-    } else {
-        shade_fragment_t<SHADER, false>(fu, ap, w0, w1, w2, diffuse, normal, sh, rgb);
+    bool bad;
+    if (ShaderAttrs<SHADER>::LIT) { /* several sqrt/reciprocal sites: worth the shared range check */
+        const uint32_t c = shade_fragment_t<SHADER, true>(fu, ap, w0, w1, w2, diffuse, normal, sh, bad);
+        if (bad) return shade_fragment_exact<SHADER>(&fu, ap, w0, w1, w2, &diffuse, &normal, &sh); /* an operand left the fast paths' range */
+        return c;
     }
-    return colour_bytes(rgb);
+    return shade_fragment_t<SHADER, false>(fu, ap, w0, w1, w2, diffuse, normal, sh, bad);
 }
 
 template <int SHADER, int MODE>
