@@ -531,7 +531,10 @@ constexpr int RW_WARPS = 4;
 #define HANA_OCC_OTHER 7
 #endif
 constexpr int RW_THREADS = RW_WARPS * 32;
-constexpr int RW_CHUNK = 32;
+#ifndef HANA_RW_CHUNK
+#define HANA_RW_CHUNK 16 /* records staged per round (and attribute blocks staged per tile): 5 + NQ float4 of shared memory each */
+#endif
+constexpr int RW_CHUNK = HANA_RW_CHUNK;
 constexpr int RW_REC_Q = 5; /* float4 per staged record */
 constexpr uint32_t ORD_NONE = 0xFFFFFFFFu;
 
@@ -539,7 +542,7 @@ constexpr uint32_t ORD_NONE = 0xFFFFFFFFu;
  *   q0 = ax, ay, s0x, s0y         q1 = s1x, s1y, uz (< 0), thr
  *   q2 = bbox centre x, centre y, half extent x, half extent y   (exact: sums of two 16-bit integers, halved)
  *   q3 = d0, d1, d2, 1/uz         q4 = triangle slot, order key, B/C exchanged flag, sub-block mask */
-template <int MODE>
+template <int MODE, int NQ>
 struct alignas(128) WarpTile {
     /* TMA sources/destinations first: each 128-byte aligned */
     uint32_t color[mode_is_r8(MODE) ? 32 : TILE_PIX]; /* box 16x16 u32; CLEAR_FOLD: holds the parked w0 of a pixel until it is shaded */
@@ -550,13 +553,16 @@ struct alignas(128) WarpTile {
     float pw2[mode_is_r8(MODE) ? 32 : TILE_PIX];
     float pw0_own[MODE == MODE_RMW ? TILE_PIX : 32];        /* RMW: color[] holds the target's pixels */
     float4 tri[RW_CHUNK * RW_REC_Q];                        /* staged raster records */
-    float4 sattr[mode_is_r8(MODE) ? RW_CHUNK * 2 : 1]; /* SHADOW_R8: their (1/w, clip z) blocks */
+    float4 sattr[mode_is_r8(MODE) ? RW_CHUNK * 2 : RW_CHUNK * NQ]; /* SHADOW_R8: the records' (1/w, clip z) blocks; otherwise, for a
+                                                                      tile whose list fits one chunk, the records' attribute blocks
+                                                                      (NQ float4 each): the shading stage reads them with LDS instead
+                                                                      of one dependent L2 round trip per sub-block */
     FragUniforms fu;                                        /* the tile's frame: what fragment() reads */
     alignas(8) uint64_t bar;
 };
-template <int MODE>
+template <int MODE, int NQ>
 struct alignas(128) RasterSmem {
-    WarpTile<MODE> w[RW_WARPS];
+    WarpTile<MODE, NQ> w[RW_WARPS];
     uint32_t clr_color[TILE_PIX]; /* constant clear tiles, TMA store source for empty tiles */
     float clr_depth[TILE_PIX];
     alignas(128) uint8_t clr_r8[TILE_PIX];
@@ -564,8 +570,8 @@ struct alignas(128) RasterSmem {
 
 /* The 32 (frame,tile) slots [base, base+32): those no triangle touches are cleared by TMA, two
  * fire-and-forget bulk stores per lane from the constant tiles. */
-template <int MODE>
-__device__ __forceinline__ void clear_slots(const RasterParams& q, RasterSmem<MODE>& sm, const CUtensorMap& tm_color,
+template <int MODE, int NQ>
+__device__ __forceinline__ void clear_slots(const RasterParams& q, RasterSmem<MODE, NQ>& sm, const CUtensorMap& tm_color,
                                             const CUtensorMap& tm_depth, const CUtensorMap& tm_r8, uint32_t base,
                                             uint32_t n_slots) {
     const PassParams& p = q.p;
@@ -635,24 +641,24 @@ __device__ __forceinline__ uint32_t subblock_mask(int x0, int x1, int y0, int y1
 /* graphics.cpp:362-373 for one fragment: interpolate the attributes the shader reads, run fragment(), return the R,G,B
  * bytes set_color stores (renderbuffer.cpp:38-44). The fragment stage's uniforms arrive as 128-bit loads. FAST: sqrt /
  * reciprocal fast paths with one shared range check (qsqrt); *bad tells the caller that an operand left their range. */
-template <int SHADER, bool FAST>
-__device__ __forceinline__ uint32_t shade_fragment_t(const FragUniforms& fu, const float4* ap, float w0, float w1, float w2,
+template <int SHADER, bool FAST, class Src>
+__device__ __forceinline__ uint32_t shade_fragment_t(const FragUniforms& fu, const Src ap, float w0, float w1, float w2,
                                                      const DevTexture& diffuse, const DevTexture& normal, const DevShadow& sh,
-                                                     bool& bad) {
+                                                     const void* safe, bool& bad) {
     constexpr int NA = ShaderAttrs<SHADER>::NA;
     constexpr int NQ = ShaderAttrs<SHADER>::NQ;
     bad = false;
     bool* pb = FAST ? &bad : nullptr;
     if (ShaderAttrs<SHADER>::LIT) {
         const LitAttrs la = interp_lit_packed(ap, w0, w1, w2, pb);
-        return fragment_lit_packed<SHADER>(fu, la, diffuse, normal, sh, ap, pb);
+        return fragment_lit_packed<SHADER>(fu, la, diffuse, normal, sh, safe, pb);
     }
-    const float4 rw = __ldg(ap);
+    const float4 rw = ap.load(0);
     VaryingWeights vw = varying_weights(w0, w1, w2, rw.x, rw.y, rw.z, pb);
     float a[(NQ - 1) * 4];
 #pragma unroll
     for (int k = 0; k < NQ - 1; k++) {
-        float4 v = __ldg(ap + 1 + k);
+        float4 v = ap.load(1 + k);
         a[4 * k] = v.x;
         a[4 * k + 1] = v.y;
         a[4 * k + 2] = v.z;
@@ -668,20 +674,23 @@ __device__ __forceinline__ uint32_t shade_fragment_t(const FragUniforms& fu, con
 /* The rare re-evaluation with the full sqrt / reciprocal functions. */
 template <int SHADER>
 __device__ __noinline__ uint32_t shade_fragment_exact(const FragUniforms* fu, const float4* ap, float w0, float w1, float w2,
-                                                      const DevTexture* diffuse, const DevTexture* normal, const DevShadow* sh) {
+                                                      const DevTexture* diffuse, const DevTexture* normal, const DevShadow* sh,
+                                                      const void* safe) {
     bool bad;
-    return shade_fragment_t<SHADER, false>(*fu, ap, w0, w1, w2, *diffuse, *normal, *sh, bad);
+    return shade_fragment_t<SHADER, false>(*fu, AttrGeneric{ap}, w0, w1, w2, *diffuse, *normal, *sh, safe, bad);
 }
-template <int SHADER>
-__device__ __forceinline__ uint32_t shade_fragment(const FragUniforms& fu, const float4* ap, float w0, float w1, float w2,
-                                                   const DevTexture& diffuse, const DevTexture& normal, const DevShadow& sh) {
+/* safe: any readable global address (shadow_probe loads from it unconditionally when there is no texel to fetch) */
+template <int SHADER, class Src>
+__device__ __forceinline__ uint32_t shade_fragment(const FragUniforms& fu, const Src ap, float w0, float w1, float w2,
+                                                   const DevTexture& diffuse, const DevTexture& normal, const DevShadow& sh,
+                                                   const void* safe) {
     bool bad;
     if (ShaderAttrs<SHADER>::LIT) { /* several sqrt/reciprocal sites: worth the shared range check */
-        const uint32_t c = shade_fragment_t<SHADER, true>(fu, ap, w0, w1, w2, diffuse, normal, sh, bad);
-        if (bad) return shade_fragment_exact<SHADER>(&fu, ap, w0, w1, w2, &diffuse, &normal, &sh); /* an operand left the fast paths' range */
+        const uint32_t c = shade_fragment_t<SHADER, true>(fu, ap, w0, w1, w2, diffuse, normal, sh, safe, bad);
+        if (bad) return shade_fragment_exact<SHADER>(&fu, ap.generic(), w0, w1, w2, &diffuse, &normal, &sh, safe); /* an operand left the fast paths' range */
         return c;
     }
-    return shade_fragment_t<SHADER, false>(fu, ap, w0, w1, w2, diffuse, normal, sh, bad);
+    return shade_fragment_t<SHADER, false>(fu, ap, w0, w1, w2, diffuse, normal, sh, safe, bad);
 }
 
 template <int SHADER, int MODE>
@@ -698,10 +707,10 @@ __global__ void __launch_bounds__(RW_THREADS, ShaderAttrs<SHADER>::LIT ? HANA_OC
     constexpr bool INLOOP = mode_is_r8(MODE);
     constexpr bool WIDE = (MODE == MODE_SHADOW_R8_WIDE);
     constexpr uint32_t SLOT_MASK = (INLOOP && !WIDE) ? 0x00FFFFFFu : 0xFFFFFFFFu;
-    __shared__ RasterSmem<MODE> sm;
+    __shared__ RasterSmem<MODE, NQ> sm;
     const PassParams& p = q.p;
     const unsigned lane = threadIdx.x & 31u, wid = __shfl_sync(FULL, threadIdx.x >> 5, 0); /* the broadcast lets ptxas keep the warp's shared-memory base in a uniform register instead of rebuilding it from S2R in the record loop */
-    WarpTile<MODE>& wt = sm.w[wid];
+    WarpTile<MODE, NQ>& wt = sm.w[wid];
     const int lx = (int)(lane & 7u), ly = (int)(lane >> 3);
     const bool tma = q.use_tma != 0;
     float* const pw0 = MODE == MODE_RMW ? wt.pw0_own : reinterpret_cast<float*>(wt.color);
@@ -801,9 +810,13 @@ __global__ void __launch_bounds__(RW_THREADS, ShaderAttrs<SHADER>::LIT ? HANA_OC
 
         /* Equal depths (rare): graphics.cpp:359 is "skip if z > stored" in submission order, so a fragment as deep as the
          * target's value passes (LEQUAL) and of two equally deep fragments the later submission wins. */
+        /* A tile whose whole list fits one chunk (the common case) parks the record's index in the chunk instead of the
+         * triangle's slot in the frame: its staged record (order key) and staged attribute block are then one LDS away. */
+        const bool single = !INLOOP && cnt <= (uint32_t)RW_CHUNK; /* warp-uniform */
         auto wins_tie = [&](const int sb, const uint32_t key) -> bool {
             if (bj[sb] == ORD_NONE) return true;
-            const uint32_t kb = __float_as_uint(__ldg(frame_rec + (size_t)(bj[sb] & SLOT_MASK) * 4 + 2).w);
+            const uint32_t kb = single ? __float_as_uint(wt.tri[bj[sb] * RW_REC_Q + 4].y)
+                                       : __float_as_uint(__ldg(frame_rec + (size_t)(bj[sb] & SLOT_MASK) * 4 + 2).w);
             return key > kb;
         };
 
@@ -828,10 +841,18 @@ __global__ void __launch_bounds__(RW_THREADS, ShaderAttrs<SHADER>::LIT ? HANA_OC
                 dst[1] = a1;
                 dst[2] = make_float4((float)(x0 + x1) * 0.5f, (float)(y0 + y1) * 0.5f, (float)(x1 - x0) * 0.5f, (float)(y1 - y0) * 0.5f);
                 dst[3] = swapped != 0.f ? make_float4(a3.x, a3.y, a3.z, -a3.w) : a3;
-                dst[4] = make_float4(a2.z, a2.w, swapped, __uint_as_float(mask));
+                dst[4] = make_float4(single ? __uint_as_float(lane) : a2.z, a2.w, swapped, __uint_as_float(mask));
+                if (single) {
+                    const float4* ap = frame_attr + (size_t)__float_as_uint(a2.z) * NQ;
+#pragma unroll
+                    for (int k = 0; k < NQ; k++) wt.sattr[lane * NQ + k] = __ldg(ap + k);
+                }
                 if (INLOOP) {
                     const float4* ap = p.tri_attr + ((size_t)f * p.tri_cap + __float_as_uint(a2.z)) * 2;
-                    wt.sattr[lane * 2] = __ldg(ap);
+                    float4 rw = __ldg(ap);
+                    /* all three 1/w exactly 1 (an orthographic light: lmvp's last row is (0,0,0,1)): flag it in the unused fourth float */
+                    rw.w = (rw.x == 1.f && rw.y == 1.f && rw.z == 1.f) ? 1.f : 0.f;
+                    wt.sattr[lane * 2] = rw;
                     wt.sattr[lane * 2 + 1] = __ldg(ap + 1);
                 }
             }
@@ -898,9 +919,15 @@ __global__ void __launch_bounds__(RW_THREADS, ShaderAttrs<SHADER>::LIT ? HANA_OC
                                 if (winA || winB) { /* ShadowShader::fragment IShader.cpp:176-180 on the winning fragments */
                                     const float4 rw = wt.sattr[j * 2], a = wt.sattr[j * 2 + 1];
                                     /* interpolate_varyings graphics.cpp:205-220 for clip_pos.z */
-                                    const f2 V0 = f2_mul(f2_dup(rw.x), W0), V1 = f2_mul(f2_dup(rw.y), W1), V2 = f2_mul(f2_dup(rw.z), W2);
-                                    const f2 SUM = f2_add(f2_add(V0, V1), V2);
-                                    const f2 NORM = f2_rcp(SUM);
+                                    f2 V0 = W0, V1 = W1, V2 = W2, NORM; /* 1/w == 1: the products are the weights themselves */
+                                    if (rw.w != 0.f) { /* warp-uniform. The weights of a covered pixel are >= 0 and sum to 1 within a few ulps: no range check */
+                                        NORM = f2_rcp_normal(f2_add(f2_add(V0, V1), V2));
+                                    } else {
+                                        V0 = f2_mul(f2_dup(rw.x), W0);
+                                        V1 = f2_mul(f2_dup(rw.y), W1);
+                                        V2 = f2_mul(f2_dup(rw.z), W2);
+                                        NORM = f2_rcp(f2_add(f2_add(V0, V1), V2));
+                                    }
                                     const f2 AT = f2_mul(f2_add(f2_add(f2_mul(f2_dup(a.x), V0), f2_mul(f2_dup(a.y), V1)), f2_mul(f2_dup(a.z), V2)), NORM);
                                     if (WIDE) {
                                         if (winA) bb[ia >> 2] = put_byte<ia & 3>(bb[ia >> 2], shadow_byte(f2_lo(AT)));
@@ -998,9 +1025,13 @@ __global__ void __launch_bounds__(RW_THREADS, ShaderAttrs<SHADER>::LIT ? HANA_OC
             }
             if (slot != ORD_NONE) {
                 const float w0 = pw0[pix], w1 = wt.pw1[pix], w2 = wt.pw2[pix];
-                const float4* ap = frame_attr + (size_t)slot * NQ;
-                col = (col & 0xFF000000u) | shade_fragment<SHADER>(wt.fu, ap, w0, w1, w2, q.diffuse, q.normal, sh); /* alpha is never written: renderbuffer.cpp:38-44 */
-                if (q.primid && f == 0) q.primid[(size_t)py * p.W + px] = __float_as_uint(__ldg(frame_rec + (size_t)slot * 4 + 2).w);
+                uint32_t rgb;
+                if (single) rgb = shade_fragment<SHADER>(wt.fu, AttrShared{wt.sattr + slot * NQ}, w0, w1, w2, q.diffuse, q.normal, sh, frame_attr);
+                else rgb = shade_fragment<SHADER>(wt.fu, AttrGlobal{frame_attr + (size_t)slot * NQ}, w0, w1, w2, q.diffuse, q.normal, sh, frame_attr);
+                col = (col & 0xFF000000u) | rgb; /* alpha is never written: renderbuffer.cpp:38-44 */
+                if (q.primid && f == 0)
+                    q.primid[(size_t)py * p.W + px] = single ? __float_as_uint(wt.tri[slot * RW_REC_Q + 4].y)
+                                                             : __float_as_uint(__ldg(frame_rec + (size_t)slot * 4 + 2).w);
             }
             if (q.pixels_covered) covered_acc += __popc(__ballot_sync(FULL, slot != ORD_NONE));
             if (tma) {
@@ -1034,7 +1065,7 @@ __global__ void __launch_bounds__(RW_THREADS, ShaderAttrs<SHADER>::LIT ? HANA_OC
         if (MODE != MODE_RMW && !clear_done) {
             const uint32_t base = __shfl_sync(FULL, clr_base, 0);
             if (base >= n_slots) clear_done = true;
-            else clear_slots<MODE>(q, sm, tm_color, tm_depth, tm_r8, base, n_slots);
+            else clear_slots<MODE, NQ>(q, sm, tm_color, tm_depth, tm_r8, base, n_slots);
         }
         /* advance the queue */
         e_cur = e_nxt;
@@ -1047,7 +1078,7 @@ __global__ void __launch_bounds__(RW_THREADS, ShaderAttrs<SHADER>::LIT ? HANA_OC
             if (lane == 0) base = atomicAdd(&p.counters->clear_cursor, 32u);
             base = __shfl_sync(FULL, base, 0);
             if (base >= n_slots) clear_done = true;
-            else clear_slots<MODE>(q, sm, tm_color, tm_depth, tm_r8, base, n_slots);
+            else clear_slots<MODE, NQ>(q, sm, tm_color, tm_depth, tm_r8, base, n_slots);
         }
     }
     /* shared memory must outlive the bulk stores that read it */
