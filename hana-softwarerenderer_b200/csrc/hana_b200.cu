@@ -919,7 +919,7 @@ static int run_pass(hana_ctx* ctx, const PassDesc& d) {
         if (occ <= 0) occ = 1;
     }
     size_t want = ((size_t)cnt.n_work + RW_WARPS - 1) / RW_WARPS; /* one tile per warp at a time */
-    if (d.mode != MODE_RMW) want = std::max<size_t>(want, (tiles_total + 1023) / 1024);
+    if (d.mode != MODE_RMW) want = std::max<size_t>(want, (tiles_total + 1023) / 1024); /* empty targets still need their clears */
     int blocks = (int)std::max<size_t>(1, std::min<size_t>(want, (size_t)ctx->sm_count * occ));
     static const CUtensorMap dummy = {};
     const CUtensorMap& ta = d.tm_color ? *d.tm_color : dummy;

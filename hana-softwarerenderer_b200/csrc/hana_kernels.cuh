@@ -563,45 +563,61 @@ struct alignas(128) WarpTile {
 template <int MODE, int NQ>
 struct alignas(128) RasterSmem {
     WarpTile<MODE, NQ> w[RW_WARPS];
-    uint32_t clr_color[TILE_PIX]; /* constant clear tiles, TMA store source for empty tiles */
-    float clr_depth[TILE_PIX];
-    alignas(128) uint8_t clr_r8[TILE_PIX];
 };
 
-/* The 32 (frame,tile) slots [base, base+32): those no triangle touches are cleared by TMA, two
- * fire-and-forget bulk stores per lane from the constant tiles. */
-template <int MODE, int NQ>
-__device__ __forceinline__ void clear_slots(const RasterParams& q, RasterSmem<MODE, NQ>& sm, const CUtensorMap& tm_color,
-                                            const CUtensorMap& tm_depth, const CUtensorMap& tm_r8, uint32_t base,
-                                            uint32_t n_slots) {
+/* Clear duty. Tiles no triangle touches are never rasterised, so somebody has to give them the clear values (the clear
+ * is folded into the pass: one write per pixel, no separate pass over the target). Work item i of a pass = (frame, tile
+ * row, group of CLEAR_GROUP consecutive tiles of that row); a warp takes one item per tile it rasterises until the queue
+ * is empty. The lanes read the group's tile counts, and the empty tiles are written with plain 128-bit stores, the
+ * whole warp side by side: lane = (tile of the group, 16-byte quarter of a pixel row) for the 4-byte planes, lane = tile
+ * for the 1-byte shadow maps — 32 (16) store instructions per item. (Round 1 issued one TMA box store per empty tile
+ * and plane from a constant shared-memory tile; UTMASTG takes its operands from uniform registers, so the compiler
+ * serialised the warp lane by lane: ~24 instructions per store against 4 per tile here.) */
+template <int MODE>
+struct ClearGeom {
+    static constexpr int GROUP = mode_is_r8(MODE) ? 32 : 8;
+};
+template <int MODE>
+__device__ __forceinline__ void clear_item(const RasterParams& q, uint32_t item, int groups_x) {
+    constexpr unsigned FULL = 0xFFFFFFFFu;
+    constexpr int G = ClearGeom<MODE>::GROUP;
     const PassParams& p = q.p;
-    const uint32_t s = base + (threadIdx.x & 31u);
-    const int f = (int)(s / (uint32_t)p.n_tiles), t = (int)(s % (uint32_t)p.n_tiles);
-    const int tx = t % p.tiles_x, ty = t / p.tiles_x;
-    if (s < n_slots && ty >= p.band_y0 && ty < p.band_y1 && p.tile_count[(size_t)f * p.tile_pad + tile_slot(p, t)] == 0u) {
-        if (q.use_tma) {
-            if (mode_is_r8(MODE)) {
-                tma_store_3d(&tm_r8, sm.clr_r8, tx * TILE, ty * TILE, f);
-            } else {
-                tma_store_3d(&tm_color, sm.clr_color, tx * TILE, ty * TILE, f);
-                tma_store_3d(&tm_depth, sm.clr_depth, tx * TILE, ty * TILE, f);
-            }
-            tma_commit();
-        } else {
-            for (int yy = 0; yy < TILE; yy++) {
-                const int py = ty * TILE + yy;
-                if (py >= p.H) break;
-                for (int xx = 0; xx < TILE; xx++) {
-                    const int px = tx * TILE + xx;
-                    if (px >= p.W) break;
-                    if (mode_is_r8(MODE)) {
-                        q.shadow_out[(size_t)f * q.shadow_out_frame_stride + (size_t)py * q.shadow_out_pitch + px] = 0;
-                    } else {
-                        const size_t o = (size_t)f * q.frame_stride + (size_t)py * p.W + px;
-                        q.color[o] = q.clear_color;
-                        q.depth[o] = q.clear_depth;
-                    }
+    const unsigned lane = threadIdx.x & 31u;
+    const int gx = (int)(item % (uint32_t)groups_x);
+    const uint32_t r = item / (uint32_t)groups_x;
+    const int ty = (int)(r % (uint32_t)p.tiles_y), f = (int)(r / (uint32_t)p.tiles_y);
+    if (ty < p.band_y0 || ty >= p.band_y1) return; /* warp-uniform */
+    const int tx_l = gx * G + (int)lane;
+    bool empty = false;
+    if ((int)lane < G && tx_l < p.tiles_x) empty = p.tile_count[(size_t)f * p.tile_pad + tile_slot(p, ty * p.tiles_x + tx_l)] == 0u;
+    const unsigned mask = __ballot_sync(FULL, empty);
+    if (!mask) return;
+    if (mode_is_r8(MODE)) {
+        /* rows and columns beyond the frame exist in the padded maps (pitch and height are multiples of 16) */
+        if (empty) {
+            uint8_t* dst = q.shadow_out + (size_t)f * q.shadow_out_frame_stride + (size_t)(ty * TILE) * q.shadow_out_pitch + (size_t)tx_l * TILE;
+#pragma unroll
+            for (int yy = 0; yy < TILE; yy++) *reinterpret_cast<uint4*>(dst + (size_t)yy * q.shadow_out_pitch) = make_uint4(0u, 0u, 0u, 0u);
+        }
+    } else {
+        const int t8 = (int)(lane >> 2), px = (gx * G + t8) * TILE + (int)(lane & 3u) * 4;
+        if (((mask >> t8) & 1u) && px < p.W) {
+            const int rows = min(TILE, p.H - ty * TILE);
+            const size_t o = (size_t)f * q.frame_stride + (size_t)(ty * TILE) * p.W + px;
+            if ((p.W & 3) == 0) { /* rows are 16-byte aligned */
+                const uint4 cc = make_uint4(q.clear_color, q.clear_color, q.clear_color, q.clear_color);
+                const float4 dd = make_float4(q.clear_depth, q.clear_depth, q.clear_depth, q.clear_depth);
+                for (int yy = 0; yy < rows; yy++) {
+                    *reinterpret_cast<uint4*>(q.color + o + (size_t)yy * p.W) = cc;
+                    *reinterpret_cast<float4*>(q.depth + o + (size_t)yy * p.W) = dd;
                 }
+            } else {
+                const int nx = min(4, p.W - px);
+                for (int yy = 0; yy < rows; yy++)
+                    for (int xx = 0; xx < nx; xx++) {
+                        q.color[o + (size_t)yy * p.W + xx] = q.clear_color;
+                        q.depth[o + (size_t)yy * p.W + xx] = q.clear_depth;
+                    }
             }
         }
     }
@@ -717,15 +733,10 @@ __global__ void __launch_bounds__(RW_THREADS, ShaderAttrs<SHADER>::LIT ? HANA_OC
 
     if (p.counters->pool_used > p.pool_cap) return; /* lists are incomplete: host re-runs with a larger pool */
     const uint32_t n_work = p.counters->n_work;
-    const uint32_t n_slots = (uint32_t)p.n_frames * (uint32_t)p.n_tiles;
+    const int clear_groups_x = (p.tiles_x + ClearGeom<MODE>::GROUP - 1) / ClearGeom<MODE>::GROUP;
+    const uint32_t n_clear = (uint32_t)p.n_frames * (uint32_t)p.tiles_y * (uint32_t)clear_groups_x; /* clear work items */
 
-    if (MODE != MODE_RMW) {
-        for (int i = threadIdx.x; i < TILE_PIX; i += RW_THREADS) {
-            sm.clr_color[i] = q.clear_color;
-            sm.clr_depth[i] = q.clear_depth;
-            sm.clr_r8[i] = 0;
-        }
-    } else if (lane == 0) {
+    if (MODE == MODE_RMW && lane == 0) {
         mbar_init(&wt.bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -756,7 +767,7 @@ __global__ void __launch_bounds__(RW_THREADS, ShaderAttrs<SHADER>::LIT ? HANA_OC
         if (lane == 0) {
             e_nxt = fetch_work(p, i_next, n_work);
             i_nn = atomic_add_async(&p.counters->work_cursor, 1u);
-            if (MODE != MODE_RMW && !clear_done) clr_base = atomic_add_async(&p.counters->clear_cursor, 32u);
+            if (MODE != MODE_RMW && !clear_done) clr_base = atomic_add_async(&p.counters->clear_cursor, 1u);
         }
 
         /* -- one non-empty tile -- */
@@ -1061,11 +1072,11 @@ __global__ void __launch_bounds__(RW_THREADS, ShaderAttrs<SHADER>::LIT ? HANA_OC
                 tma_commit();
             }
         }
-        /* clear duty while raster work remains: 32 (frame,tile) slots per tile rasterised */
+        /* clear duty while clear work remains: one item (a group of tiles of one tile row) per tile rasterised */
         if (MODE != MODE_RMW && !clear_done) {
-            const uint32_t base = __shfl_sync(FULL, clr_base, 0);
-            if (base >= n_slots) clear_done = true;
-            else clear_slots<MODE, NQ>(q, sm, tm_color, tm_depth, tm_r8, base, n_slots);
+            const uint32_t item = __shfl_sync(FULL, clr_base, 0);
+            if (item >= n_clear) clear_done = true;
+            else clear_item<MODE>(q, item, clear_groups_x);
         }
         /* advance the queue */
         e_cur = e_nxt;
@@ -1074,11 +1085,11 @@ __global__ void __launch_bounds__(RW_THREADS, ShaderAttrs<SHADER>::LIT ? HANA_OC
     /* raster queue drained: every warp helps with what is left of the clear queue */
     if (MODE != MODE_RMW) {
         while (!clear_done) {
-            uint32_t base = 0;
-            if (lane == 0) base = atomicAdd(&p.counters->clear_cursor, 32u);
-            base = __shfl_sync(FULL, base, 0);
-            if (base >= n_slots) clear_done = true;
-            else clear_slots<MODE, NQ>(q, sm, tm_color, tm_depth, tm_r8, base, n_slots);
+            uint32_t item = 0;
+            if (lane == 0) item = atomicAdd(&p.counters->clear_cursor, 1u);
+            item = __shfl_sync(FULL, item, 0);
+            if (item >= n_clear) clear_done = true;
+            else clear_item<MODE>(q, item, clear_groups_x);
         }
     }
     /* shared memory must outlive the bulk stores that read it */
