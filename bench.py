@@ -435,13 +435,17 @@ def main():
     def render_host(sw):
         ck(ctx.L.hana_sweep_render(sw.h, model.h, hana.BLINN, C.c_void_p(pinned_u.ptr), FE, dtex.h, ntex.h, clr, float(hana.FLT_MAX)))
 
-    def run_e2e(step_fn):
+    def run_e2e(step_fn, flush_fn=None):
         for s in range(2):
             step_fn(s)
+        if flush_fn:
+            flush_fn(2)
         barrier()
         ctx.timer_start()
         for s in range(e2e_steps):
             step_fn(s)
+        if flush_fn:
+            flush_fn(e2e_steps)
         ms_ = ctx.timer_stop()  # waits for every render and every copy
         barrier()
         return FE * e2e_steps * world / (max_over_ranks(ms_) * 1e-3)
@@ -471,18 +475,33 @@ def main():
         cap = npx * 3 * FE  # the pinned ring is as large as the raw surfaces; an RLE file of these frames is ~5x smaller
         offs = ((C.c_uint64 * (FE + 1))(), (C.c_uint64 * (FE + 1))())
 
+        szs = ((C.c_uint64 * FE)(), (C.c_uint64 * FE)())
+        state = {"pending": None}
+
+        def fetch(r):
+            ck(ctx.L.hana_sweep_fetch_tga(rings[r].h, C.c_void_p(pin_p[r].ptr), C.c_size_t(cap), offs[r], szs[r]))
+
         def step_tga(s):
+            # render + encode batch s, then hand batch s-1 (the other ring, long finished) to the copy engine: the host never
+            # waits for the batch it has just queued
             sw = rings[s & 1]
             render_host(sw)
-            ck(ctx.L.hana_sweep_encode_tga(sw.h, 0, FE, 1))
-            ck(ctx.L.hana_sweep_fetch_tga(sw.h, C.c_void_p(pin_p[s & 1].ptr), C.c_size_t(cap), offs[s & 1]))
+            ck(ctx.L.hana_sweep_encode_tga(sw.h, 0, FE))
+            if state["pending"] is not None:
+                fetch(state["pending"])
+            state["pending"] = s & 1
 
-        e2e_tga = run_e2e(step_tga)
+        def flush_tga(_n):
+            if state["pending"] is not None:
+                fetch(state["pending"])
+                state["pending"] = None
+
+        e2e_tga = run_e2e(step_tga, flush_tga)
         last = (e2e_steps - 1) & 1
         total_bytes = int(offs[last][FE])
         # byte-identity of one delivered file with the host writer (outside the timed region)
         import tempfile
-        f0 = bytes(pin_p[last].array[int(offs[last][0]):int(offs[last][1])])
+        f0 = bytes(pin_p[last].array[int(offs[last][0]):int(offs[last][0]) + int(szs[last][0])])
         gcol, _ = rings[last].download(0)
         with tempfile.TemporaryDirectory() as td:
             pth = os.path.join(td, "f.tga")

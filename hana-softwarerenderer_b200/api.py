@@ -134,6 +134,8 @@ def load():
         "hana_sweep_stats": [vp, i, vp],
         "hana_sweep_overflow_count": [vp, C.POINTER(C.c_uint64)],
         "hana_sweep_present": [vp, i, i, i, vp, C.POINTER(vp)],
+        "hana_sweep_encode_tga": [vp, i, i],
+        "hana_sweep_fetch_tga": [vp, vp, C.c_size_t, vp, vp],
         "hana_sweep_set_bands": [vp, i, i, i, i],
         "hana_sweep_render_pass": [vp, i, vp, i, vp, i, vp, vp, vp, f],
         "hana_sweep_shadow_ptrs": [vp, C.POINTER(vp), C.POINTER(i), C.POINTER(C.c_size_t)],
@@ -465,6 +467,18 @@ class Sweep:
         _ck(self.ctx.L.hana_sweep_present(self.h, first, count, fmt, _ptr(out), None))
         self.ctx.sync()
         return out
+
+    def tga_files(self, first, count):
+        """Frames [first, first+count) as RLE TGA files (bytes objects), encoded on the device: what
+        TGAImage::write_tga_file(rle=True) would write (tgaimage.cpp:145-246)."""
+        _ck(self.ctx.L.hana_sweep_encode_tga(self.h, first, count))
+        cap = count * (self.width * self.height * 3 + self.width * self.height // 64 + 2048)
+        buf = np.empty(cap, np.uint8)
+        offs = (C.c_uint64 * (count + 1))()
+        sizes = (C.c_uint64 * count)()
+        _ck(self.ctx.L.hana_sweep_fetch_tga(self.h, _ptr(buf), cap, offs, sizes))
+        self.ctx.sync()
+        return [bytes(buf[int(offs[f]):int(offs[f]) + int(sizes[f])]) for f in range(count)]
 
     def checksums(self, n_frames):
         out = np.zeros(n_frames, np.uint64)

@@ -20,6 +20,7 @@
 #include <vector>
 
 #include "hana_kernels.cuh"
+#include "hana_tga.cuh"
 
 using namespace hana;
 
@@ -57,7 +58,7 @@ struct Scratch {
     float4* tri_attr = nullptr;
     size_t tri_total = 0; /* records allocated (n_frames * tri_cap) */
     size_t attr_total = 0;
-    uint32_t* tri_count = nullptr;
+    uint32_t* tri_count = nullptr; /* [frames][TRI_COUNT_WAYS] emitted triangles, then [frames] extra slots */
     size_t frames_cap = 0;
     uint32_t* tile_arrays = nullptr; /* count | cursor | offset, each n_frames * n_tiles */
     size_t tile_arr_cap = 0;
@@ -169,6 +170,22 @@ struct hana_sweep {
     int band[2][2];                /* tile rows [first, first+count) of the shadow / main pass; count 0 = all (hana_sweep_set_bands) */
     uint8_t* present_buf;          /* device: presented frames (hana_sweep_present) */
     size_t present_cap;
+    /* RLE TGA files made on the device (hana_sweep_encode_tga / hana_sweep_fetch_tga) */
+    struct Tga {
+        uint8_t* slots = nullptr;      /* [count] worst-case slots the encoder writes */
+        uint8_t* packed = nullptr;     /* the files back to back (16-byte aligned starts) */
+        size_t cap_frames = 0, slot_bytes = 0;
+        TgaCarry* carry = nullptr;     /* [max_frames] */
+        unsigned long long* sizes = nullptr;   /* device [max_frames] */
+        unsigned long long* offsets = nullptr; /* device [max_frames + 1] */
+        unsigned int* ticket = nullptr;
+        unsigned long long* meta_pin = nullptr; /* pinned: offsets [max_frames + 1], then sizes [max_frames] */
+        cudaEvent_t ev = nullptr;
+        int first = 0, count = 0;      /* what the last encode covered */
+        uint64_t rerender_seen = 0;
+        bool valid = false;
+    } tga;
+    uint64_t rerender_count;       /* batches rendered again by sweep_verify */
     struct Pending {
         bool active = false;
         const hana_model* model = nullptr;
@@ -640,7 +657,8 @@ struct PassDesc {
     uint32_t dbg_cap = 0;
     bool setup_only = false;
     int prof_kind = PROF_RASTER_MAIN;
-    std::vector<uint32_t>* tri_counts_out = nullptr;
+    std::vector<uint32_t>* tri_counts_out = nullptr; /* triangles emitted per frame */
+    std::vector<uint32_t>* slots_out = nullptr;      /* record slots in use per frame (faces + what clipping added) */
     PassCounters* counters_out = nullptr;
     /* lazy mode (sweeps): nothing is read back inside the pass; capacities are the context's current ones and the
      * needs are accumulated in *overflow for the host to check at the sweep's next synchronisation point */
@@ -752,7 +770,7 @@ static int run_pass(hana_ctx* ctx, const PassDesc& d) {
         size_t tri_total = (size_t)tri_cap * d.n_frames;
         HANA_TRY(grow(&sc.tri_rec, &sc.tri_total, tri_total * 4, ctx));
         HANA_TRY(grow(&sc.tri_attr, &sc.attr_total, tri_total * MAX_ATTR_QUADS, ctx));
-        HANA_TRY(grow(&sc.tri_count, &sc.frames_cap, (size_t)d.n_frames, ctx));
+        HANA_TRY(grow(&sc.tri_count, &sc.frames_cap, (size_t)d.n_frames * (TRI_COUNT_WAYS + 1), ctx));
         const int tile_rows = (int)((n_tiles + 31) / 32);
         const size_t tiles_pad_total = (size_t)tile_rows * 32 * d.n_frames;
         HANA_TRY(grow(&sc.tile_arrays, &sc.tile_arr_cap, tiles_pad_total * 2 + tiles_total, ctx));
@@ -775,6 +793,7 @@ static int run_pass(hana_ctx* ctx, const PassDesc& d) {
         p.tri_attr = sc.tri_attr;
         p.tri_cap = tri_cap;
         p.tri_count = sc.tri_count;
+        p.tri_extra = sc.tri_count + (size_t)d.n_frames * TRI_COUNT_WAYS;
         p.tile_count = sc.tile_arrays;
         p.tile_cursor = sc.tile_arrays + tiles_pad_total;
         p.tile_offset = sc.tile_arrays + 2 * tiles_pad_total;
@@ -789,7 +808,7 @@ static int run_pass(hana_ctx* ctx, const PassDesc& d) {
 
         /* zero: counters, per-frame triangle counts, tile counts + cursors (contiguous) */
         CU_TRY(cudaMemsetAsync(sc.counters, 0, sizeof(PassCounters), st));
-        CU_TRY(cudaMemsetAsync(sc.tri_count, 0, sizeof(uint32_t) * d.n_frames, st));
+        CU_TRY(cudaMemsetAsync(sc.tri_count, 0, sizeof(uint32_t) * d.n_frames * (TRI_COUNT_WAYS + 1), st));
         CU_TRY(cudaMemsetAsync(sc.tile_arrays, 0, sizeof(uint32_t) * 2 * tiles_pad_total, st));
 
         cudaEvent_t ea, eb;
@@ -836,8 +855,8 @@ static int run_pass(hana_ctx* ctx, const PassDesc& d) {
             if (d.counters_pinned)
                 CU_TRY(cudaMemcpyAsync(d.counters_pinned, sc.counters, sizeof(PassCounters), cudaMemcpyDeviceToHost, st));
             if (d.tri_counts_pinned)
-                CU_TRY(cudaMemcpyAsync(d.tri_counts_pinned, sc.tri_count, sizeof(uint32_t) * d.n_frames, cudaMemcpyDeviceToHost,
-                                       st));
+                CU_TRY(cudaMemcpyAsync(d.tri_counts_pinned, sc.tri_count, sizeof(uint32_t) * d.n_frames * TRI_COUNT_WAYS,
+                                       cudaMemcpyDeviceToHost, st));
             if (d.tri_cap_used) *d.tri_cap_used = tri_cap;
             if (d.pool_cap_used) *d.pool_cap_used = p.pool_cap;
             lists_ready = true;
@@ -863,10 +882,16 @@ static int run_pass(hana_ctx* ctx, const PassDesc& d) {
     const PassCounters cnt = *sc.counters_host;
     if (d.counters_out) *d.counters_out = cnt;
     if (d.tri_counts_out && !d.lazy) {
-        d.tri_counts_out->resize(d.n_frames);
-        CU_TRY(cudaMemcpyAsync(d.tri_counts_out->data(), sc.tri_count, sizeof(uint32_t) * d.n_frames, cudaMemcpyDeviceToHost,
-                               st));
+        std::vector<uint32_t> ways((size_t)d.n_frames * (TRI_COUNT_WAYS + 1));
+        CU_TRY(cudaMemcpyAsync(ways.data(), sc.tri_count, sizeof(uint32_t) * ways.size(), cudaMemcpyDeviceToHost, st));
         CU_TRY(cudaStreamSynchronize(st));
+        d.tri_counts_out->assign(d.n_frames, 0u);
+        for (int fi = 0; fi < d.n_frames; fi++)
+            for (int w = 0; w < TRI_COUNT_WAYS; w++) (*d.tri_counts_out)[fi] += ways[(size_t)fi * TRI_COUNT_WAYS + w];
+        if (d.slots_out) {
+            d.slots_out->assign(d.n_frames, 0u);
+            for (int fi = 0; fi < d.n_frames; fi++) (*d.slots_out)[fi] = (uint32_t)nfaces + ways[(size_t)d.n_frames * TRI_COUNT_WAYS + fi];
+        }
     }
     if (d.setup_only) return HANA_OK;
 
@@ -1099,6 +1124,7 @@ extern "C" int hana_sweep_create(hana_ctx* ctx, int width, int height, int max_f
     for (auto& e : s->ev_check) e = nullptr;
     s->check_tail = s->n_checks = s->next_slot = 0;
     s->overflow_batches = 0;
+    s->rerender_count = 0;
     cudaError_t e = cudaMalloc(&s->color, n * 4 * max_frames);
     if (e == cudaSuccess) e = cudaMalloc(&s->depth, n * 4 * max_frames);
     if (e == cudaSuccess) e = cudaMalloc(&s->shadow_r8, s->shadow_frame_bytes * max_frames);
@@ -1108,7 +1134,7 @@ extern "C" int hana_sweep_create(hana_ctx* ctx, int width, int height, int max_f
     if (e == cudaSuccess) e = cudaMalloc(&s->pix_counts, sizeof(uint32_t) * max_frames);
     if (e == cudaSuccess) e = cudaMalloc(&s->overflow, sizeof(OverflowRecord));
     if (e == cudaSuccess) e = cudaMallocHost(&s->pin, sizeof(*s->pin));
-    if (e == cudaSuccess) e = cudaMallocHost(&s->tri_counts_pin, sizeof(uint32_t) * 2 * max_frames);
+    if (e == cudaSuccess) e = cudaMallocHost(&s->tri_counts_pin, sizeof(uint32_t) * 2 * max_frames * TRI_COUNT_WAYS);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev_render, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev_copy, cudaEventDisableTiming);
     for (auto& ev : s->ev_check)
@@ -1145,6 +1171,10 @@ extern "C" int hana_sweep_destroy(hana_sweep* s) {
     if (s->tri_counts_pin) cudaFreeHost(s->tri_counts_pin);
     if (s->ev_render) cudaEventDestroy(s->ev_render);
     if (s->ev_copy) cudaEventDestroy(s->ev_copy);
+    cudaFree(s->tga.slots); cudaFree(s->tga.packed); cudaFree(s->tga.carry); cudaFree(s->tga.sizes); cudaFree(s->tga.offsets);
+    cudaFree(s->tga.ticket);
+    if (s->tga.meta_pin) cudaFreeHost(s->tga.meta_pin);
+    if (s->tga.ev) cudaEventDestroy(s->tga.ev);
     for (auto ev : s->ev_check)
         if (ev) cudaEventDestroy(ev);
     if (ctx->host_sweep == s) ctx->host_sweep = nullptr;
@@ -1234,7 +1264,7 @@ static int sweep_render_passes(hana_sweep* s, const hana_model* model, int shade
     d.tri_counts_out = &s->last_tri_counts[1];
     d.lazy = lazy;
     d.overflow = s->overflow;
-    d.tri_counts_pinned = s->tri_counts_pin + s->max_frames;
+    d.tri_counts_pinned = s->tri_counts_pin + (size_t)s->max_frames * TRI_COUNT_WAYS;
     d.counters_pinned = &s->pin->counters[1];
     uint32_t tc = 0, pc = 0;
     d.tri_cap_used = &tc;
@@ -1310,13 +1340,16 @@ static int sweep_verify(hana_sweep* s) {
     s->pending.active = false;
     const OverflowRecord need = s->pin->need[pd.slot];
     for (int pass = 0; pass < 2; pass++) {
-        s->last_tri_counts[pass].assign(s->tri_counts_pin + (size_t)pass * s->max_frames,
-                                        s->tri_counts_pin + (size_t)pass * s->max_frames + pd.n_frames);
+        const uint32_t* ways = s->tri_counts_pin + (size_t)pass * s->max_frames * TRI_COUNT_WAYS;
+        s->last_tri_counts[pass].assign(pd.n_frames, 0u);
+        for (int fi = 0; fi < pd.n_frames; fi++)
+            for (int w = 0; w < TRI_COUNT_WAYS; w++) s->last_tri_counts[pass][fi] += ways[(size_t)fi * TRI_COUNT_WAYS + w];
     }
     s->last_stats.tile_refs = s->pin->counters[1].pool_used;
     s->last_stats.tiles_touched = s->pin->counters[1].tiles_touched;
     if (need.tri_needed <= pd.tri_cap && need.pool_needed <= pd.pool_cap) return HANA_OK;
     HANA_TRY(grow_scratch_for(ctx, need));
+    s->rerender_count++;
     return sweep_render_passes(s, pd.model, pd.shader, pd.enable_shadow, pd.n_frames, pd.diffuse, pd.normal, pd.clear_rgba,
                                pd.clear_depth, false);
 }
@@ -1584,6 +1617,98 @@ extern "C" int hana_sweep_present(hana_sweep* s, int first, int count, int forma
     }
     return HANA_OK;
 }
+/* ---- RLE TGA files of the frames, made on the device (hana_tga.cuh) ---------------------------------------------- */
+static int tga_encode_launch(hana_sweep* s, int first, int count) {
+    hana_ctx* ctx = s->ctx;
+    hana_sweep::Tga& t = s->tga;
+    const size_t npix = (size_t)s->w * s->h;
+    const size_t slot_bytes = tga_slot_bytes(npix);
+    if (s->copy_in_flight) { /* the previous fetch reads the packed buffer */
+        CU_TRY(cudaStreamWaitEvent(ctx->stream, s->ev_copy, 0));
+        s->copy_in_flight = false;
+    }
+    const unsigned chunks = (unsigned)((npix + TGA_CHUNK - 1) / TGA_CHUNK);
+    if (!t.sizes) {
+        CU_TRY(cudaMalloc(&t.sizes, sizeof(unsigned long long) * s->max_frames));
+        CU_TRY(cudaMalloc(&t.offsets, sizeof(unsigned long long) * (s->max_frames + 1)));
+        CU_TRY(cudaMalloc(&t.ticket, sizeof(unsigned int)));
+        CU_TRY(cudaMallocHost(&t.meta_pin, sizeof(unsigned long long) * (2 * (size_t)s->max_frames + 1)));
+        CU_TRY(cudaEventCreateWithFlags(&t.ev, cudaEventDisableTiming));
+    }
+    if ((size_t)count > t.cap_frames || slot_bytes != t.slot_bytes) {
+        CU_TRY(cudaStreamSynchronize(ctx->stream));
+        CU_TRY(cudaStreamSynchronize(ctx->copy_stream));
+        cudaFree(t.slots);
+        cudaFree(t.packed);
+        cudaFree(t.carry);
+        t.slots = t.packed = nullptr;
+        t.carry = nullptr;
+        t.cap_frames = 0;
+        CU_TRY(cudaMalloc(&t.carry, sizeof(TgaCarry) * (size_t)count * (chunks + 1))); /* one mailbox per (frame, chunk) */
+        CU_TRY(cudaMalloc(&t.slots, slot_bytes * count));
+        CU_TRY(cudaMalloc(&t.packed, slot_bytes * count));
+        t.cap_frames = (size_t)count;
+        t.slot_bytes = slot_bytes;
+    }
+    CU_TRY(cudaMemsetAsync(t.ticket, 0, sizeof(unsigned int), ctx->stream));
+    CU_TRY(cudaMemsetAsync(t.carry, 0, sizeof(TgaCarry) * (size_t)count * (chunks + 1), ctx->stream));
+    cudaEvent_t a, b;
+    prof_begin(ctx, PROF_OTHER, &a, &b);
+    tga_rle_kernel<<<chunks * (unsigned)count, TGA_THREADS, 0, ctx->stream>>>(s->color, npix, first, s->w, s->h, count, t.slots, slot_bytes,
+                                                                          t.carry, t.sizes, t.ticket);
+    tga_offsets_kernel<<<1, 32, 0, ctx->stream>>>(t.sizes, t.offsets, count);
+    tga_pack_kernel<<<dim3(64, (unsigned)count), 256, 0, ctx->stream>>>(t.slots, slot_bytes, t.sizes, t.offsets, t.packed);
+    prof_end(ctx, PROF_OTHER, a, b);
+    ctx->launches += 3;
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaMemcpyAsync(t.meta_pin, t.offsets, sizeof(unsigned long long) * (count + 1), cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(cudaMemcpyAsync(t.meta_pin + s->max_frames + 1, t.sizes, sizeof(unsigned long long) * count, cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(cudaEventRecord(t.ev, ctx->stream));
+    t.first = first;
+    t.count = count;
+    t.rerender_seen = s->rerender_count;
+    t.valid = true;
+    return HANA_OK;
+}
+
+/* Queues the encoding of frames [first, first+count) of the sweep's last render as RLE-compressed 24-bit TGA files
+ * (TGAImage::write_tga_file(rle = true), tgaimage.cpp:145-246: byte-identical). Asynchronous, ordered after the render on
+ * the context's stream; nothing is read back. */
+extern "C" int hana_sweep_encode_tga(hana_sweep* s, int first, int count) {
+    if (!s) return fail(HANA_E_INVALID, "sweep is NULL");
+    if (first < 0 || count < 1 || first + count > s->max_frames) return fail(HANA_E_INVALID, "frame range out of bounds");
+    if (s->w > 32767 || s->h > 32767) return fail(HANA_E_INVALID, "TGA: image larger than 32767 pixels on a side");
+    HANA_TRY(use_device(s->ctx));
+    return tga_encode_launch(s, first, count);
+}
+
+/* Delivers the files of the last hana_sweep_encode_tga: waits for the encoder (and for the render it followed: a batch
+ * that ran out of scratch is rendered and encoded again first), writes offsets[0..count] (file f occupies
+ * dst_host[offsets[f], offsets[f] + sizes[f]); starts are 16-byte aligned; offsets[count] = bytes used) and sizes[0..count)
+ * (may be NULL), and copies the bytes to dst_host (pinned memory overlaps the next batch) on the copy stream: complete
+ * after hana_sync() / hana_timer_stop(). HANA_E_OVERFLOW if dst_capacity is too small (hana_last_error names the need). */
+extern "C" int hana_sweep_fetch_tga(hana_sweep* s, uint8_t* dst_host, size_t dst_capacity, uint64_t* offsets, uint64_t* sizes) {
+    if (!s || !dst_host || !offsets) return fail(HANA_E_INVALID, "NULL argument");
+    hana_ctx* ctx = s->ctx;
+    hana_sweep::Tga& t = s->tga;
+    if (!t.valid) return fail(HANA_E_INVALID, "no hana_sweep_encode_tga to fetch");
+    HANA_TRY(use_device(ctx));
+    HANA_TRY(sweep_verify(s));
+    if (t.rerender_seen != s->rerender_count) HANA_TRY(tga_encode_launch(s, t.first, t.count)); /* the frames were rendered again */
+    CU_TRY(cudaEventSynchronize(t.ev));
+    const unsigned long long total = t.meta_pin[t.count];
+    if (total > dst_capacity)
+        return fail(HANA_E_OVERFLOW, "TGA files need " + std::to_string(total) + " bytes, destination holds " + std::to_string(dst_capacity));
+    for (int f = 0; f <= t.count; f++) offsets[f] = t.meta_pin[f];
+    if (sizes)
+        for (int f = 0; f < t.count; f++) sizes[f] = t.meta_pin[s->max_frames + 1 + f];
+    CU_TRY(cudaStreamWaitEvent(ctx->copy_stream, t.ev, 0));
+    CU_TRY(cudaMemcpyAsync(dst_host, t.packed, total, cudaMemcpyDeviceToHost, ctx->copy_stream));
+    CU_TRY(cudaEventRecord(s->ev_copy, ctx->copy_stream));
+    s->copy_in_flight = true;
+    return HANA_OK;
+}
+
 extern "C" int hana_sweep_device_ptrs(hana_sweep* s, void** color_dev, void** depth_dev, size_t* frame_stride_pixels) {
     if (!s) return fail(HANA_E_INVALID, "sweep is NULL");
     HANA_TRY(use_device(s->ctx));
@@ -1722,8 +1847,9 @@ extern "C" int hana_stage_setup(hana_ctx* ctx, const hana_model* model, int shad
     d.dbg_v2f = dbg;
     d.dbg_cap = (uint32_t)capacity;
     d.setup_only = true;
-    std::vector<uint32_t> tri_counts;
+    std::vector<uint32_t> tri_counts, slots;
     d.tri_counts_out = &tri_counts;
+    d.slots_out = &slots;
     uint32_t saved_hint = ctx->tri_cap_hint;
     ctx->tri_cap_hint = 0;
     int r = run_pass(ctx, d);
@@ -1732,18 +1858,23 @@ extern "C" int hana_stage_setup(hana_ctx* ctx, const hana_model* model, int shad
         cudaFree(dbg);
         return r;
     }
-    uint32_t n = tri_counts.empty() ? 0 : tri_counts[0];
-    std::vector<float> recs((size_t)n * 16);
-    std::vector<float> v2f((size_t)n * 39);
+    const uint32_t nslots = slots.empty() ? 0 : std::min<uint32_t>(slots[0], (uint32_t)capacity); /* slot = face index, or beyond for clipped fans */
+    std::vector<float> recs((size_t)nslots * 16);
+    std::vector<float> v2f((size_t)nslots * 39);
     cudaError_t e = cudaSuccess;
-    if (n) {
-        e = cudaMemcpy(recs.data(), ctx->sc.tri_rec, sizeof(float) * 16 * n, cudaMemcpyDeviceToHost);
-        if (e == cudaSuccess) e = cudaMemcpy(v2f.data(), dbg, (size_t)n * 39 * 4, cudaMemcpyDeviceToHost);
+    if (nslots) {
+        e = cudaMemcpy(recs.data(), ctx->sc.tri_rec, sizeof(float) * 16 * nslots, cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess) e = cudaMemcpy(v2f.data(), dbg, (size_t)nslots * 39 * 4, cudaMemcpyDeviceToHost);
     }
     cudaFree(dbg);
     if (e != cudaSuccess) return fail(HANA_E_CUDA, cudaGetErrorString(e));
-    std::vector<uint32_t> idx(n);
-    for (uint32_t i = 0; i < n; i++) idx[i] = i;
+    std::vector<uint32_t> idx;
+    for (uint32_t i = 0; i < nslots; i++) { /* slots of faces that emitted nothing carry the empty pixel range */
+        uint32_t bby;
+        memcpy(&bby, &recs[(size_t)i * 16 + 9], 4);
+        if (bby != DEAD_BBY) idx.push_back(i);
+    }
+    const uint32_t n = (uint32_t)idx.size();
     auto key_of = [&](uint32_t i) {
         uint32_t k;
         memcpy(&k, &recs[(size_t)i * 16 + 11], 4);

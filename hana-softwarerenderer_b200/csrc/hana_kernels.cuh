@@ -39,6 +39,8 @@ constexpr int TILE_BITS = 20;        /* work item = frame << 20 | tile_y << 10 |
 constexpr uint32_t TILE_MASK = (1u << TILE_BITS) - 1u;
 constexpr uint32_t WORK_INVALID = 0xFFFFFFFFu;
 constexpr int SETUP_THREADS = 256;
+constexpr int TRI_COUNT_WAYS = 32;   /* per-frame statistics counters: one atomic per warp, spread so that they do not queue on one address */
+constexpr uint32_t DEAD_BBY = 0x0000FFFFu; /* bby of a slot that holds no triangle (y0 = 0xFFFF > y1 = 0: an empty range for every consumer) */
 constexpr int SCAN_THREADS = 1024;
 
 enum RasterMode {
@@ -83,8 +85,9 @@ struct PassParams {
     /* scratch */
     float4* tri_rec;      /* [n_frames][tri_cap][4]: raster records */
     float4* tri_attr;     /* [n_frames][tri_cap][attr_quads] */
-    uint32_t tri_cap;
-    uint32_t* tri_count;  /* [n_frames] */
+    uint32_t tri_cap;     /* slots per frame: slot = face index for an unclipped face, slots >= nfaces for what clipping emits */
+    uint32_t* tri_count;  /* [n_frames][TRI_COUNT_WAYS] triangles emitted (statistics only; spread over several counters) */
+    uint32_t* tri_extra;  /* [n_frames] slots allocated beyond nfaces by the clipped path */
     uint32_t* tile_count; /* [n_frames][tile_pad], indexed through tile_slot(): see there */
     uint32_t* tile_offset; /* [n_frames][n_tiles] */
     uint32_t* tile_cursor; /* [n_frames][tile_pad], tile_slot() */
@@ -266,7 +269,8 @@ __device__ __noinline__ void setup_clipped(const PassParams& p, int f, int face,
         const float* c = poly + V2F_N * (j + 2);
         TriRecord r;
         if (!triangle_setup(a, b, c, p.W, p.H, (uint32_t)face * 8u + (uint32_t)j, r)) continue;
-        uint32_t slot = atomicAdd(p.tri_count + f, 1u);
+        const uint32_t slot = (uint32_t)p.nfaces + atomicAdd(p.tri_extra + f, 1u); /* a clipped face's triangles live behind the per-face slots */
+        atomicAdd(p.tri_count + (size_t)f * TRI_COUNT_WAYS + (face & (TRI_COUNT_WAYS - 1)), 1u);
         if (slot < p.tri_cap) {
             store_triangle<SHADER>(p, f, slot, r, a, b, c);
             count_single_tile(p, f, r);
@@ -278,7 +282,7 @@ template <int SHADER>
 /* `p` is __grid_constant__: the rare clipped path takes its address (a __noinline__ call), and without the qualifier
  * every thread first copies all of PassParams to local memory. For the same reason the 39 vertex-stage floats are
  * copied to a second array only on that path, so the common path keeps them in registers. */
-__global__ void __launch_bounds__(SETUP_THREADS) setup_kernel(const __grid_constant__ PassParams p) {
+__global__ void __launch_bounds__(SETUP_THREADS, 3) setup_kernel(const __grid_constant__ PassParams p) {
     const int f = blockIdx.y;
     const int face = blockIdx.x * SETUP_THREADS + threadIdx.x;
     const unsigned lane = threadIdx.x & 31u;
@@ -303,38 +307,21 @@ __global__ void __launch_bounds__(SETUP_THREADS) setup_kernel(const __grid_const
             setup_clipped<SHADER>(p, f, face, vc);
         }
     }
-    /* shuffle prefix sum over the emit flags per warp, warp totals combined in shared memory -> ONE slot-allocation
-     * atomic per CTA (a dense mesh has millions of faces per frame, all allocating from the same counter) */
-    __shared__ uint32_t s_warp_total[SETUP_THREADS / 32];
-    __shared__ uint32_t s_cta_base;
-    const unsigned wid = threadIdx.x >> 5;
-    int incl = emit ? 1 : 0;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        int t = __shfl_up_sync(0xFFFFFFFFu, incl, d);
-        if ((int)lane >= d) incl += t;
-    }
-    if (lane == 31) s_warp_total[wid] = (uint32_t)incl;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        uint32_t total = 0;
-#pragma unroll
-        for (int w = 0; w < SETUP_THREADS / 32; w++) {
-            const uint32_t t = s_warp_total[w];
-            s_warp_total[w] = total; /* exclusive */
-            total += t;
-        }
-        s_cta_base = total ? atomicAdd(p.tri_count + f, total) : 0u;
-    }
-    __syncthreads();
+    /* The triangle of an unclipped face lives in slot = face index: no slot allocation, hence no atomic and no CTA
+     * barrier (round 1 compacted the survivors with a block scan; its two barriers held 40 % of this kernel's stall
+     * samples on a 10 M-face mesh). A face that emits nothing here (culled, degenerate, or clipped: its fan lives in
+     * slots >= nfaces) marks its slot empty; the pair kernels skip it by its empty pixel range. */
     int key = -1;
-    if (emit) {
-        const uint32_t slot = s_cta_base + s_warp_total[wid] + (uint32_t)(incl - 1);
-        if (slot < p.tri_cap) {
-            store_triangle<SHADER>(p, f, slot, r, v, v + V2F_N, v + 2 * V2F_N);
+    if (face < p.nfaces && (uint32_t)face < p.tri_cap) {
+        if (emit) {
+            store_triangle<SHADER>(p, f, (uint32_t)face, r, v, v + V2F_N, v + 2 * V2F_N);
             key = single_tile_slot(p, r);
+        } else {
+            p.tri_rec[((size_t)f * p.tri_cap + (uint32_t)face) * 4 + 2] = make_float4(0.f, __uint_as_float(DEAD_BBY), 0.f, 0.f);
         }
     }
+    const unsigned live = __ballot_sync(0xFFFFFFFFu, emit);
+    if (lane == 0 && live) atomicAdd(p.tri_count + (size_t)f * TRI_COUNT_WAYS + (blockIdx.x & (TRI_COUNT_WAYS - 1)), (uint32_t)__popc(live));
     count_aggregated(p.tile_count + (size_t)f * p.tile_pad, key);
 }
 
@@ -389,8 +376,9 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_kernel(PassParams p) {
         atomicAdd(&p.counters->tiles_touched, s_total_ne);
         if (p.overflow) atomicMax(&p.overflow->pool_needed, s_base_refs + s_total_refs);
         if (blockIdx.x == 0) {
-            atomicMax(&p.counters->tri_needed, p.tri_count[f]);
-            if (p.overflow) atomicMax(&p.overflow->tri_needed, p.tri_count[f]);
+            const uint32_t slots = (uint32_t)p.nfaces + p.tri_extra[f];
+            atomicMax(&p.counters->tri_needed, slots);
+            if (p.overflow) atomicMax(&p.overflow->tri_needed, slots);
         }
     }
     __syncthreads();
@@ -425,7 +413,7 @@ __global__ void __launch_bounds__(256) pairs_kernel(PassParams p) {
     const int f = blockIdx.y;
     const uint32_t i = blockIdx.x * 256u + threadIdx.x;
     const unsigned lane = threadIdx.x & 31u;
-    uint32_t n = p.tri_count[f];
+    uint32_t n = (uint32_t)p.nfaces + p.tri_extra[f];      /* slots in use */
     if (n > p.tri_cap) n = p.tri_cap;
     if ((i & ~31u) >= n) return;                            /* whole warp past the end */
     if (FILL && p.counters->pool_used > p.pool_cap) return; /* host re-runs the pass with a larger pool */

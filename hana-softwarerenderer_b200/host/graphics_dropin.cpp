@@ -28,10 +28,20 @@
 
 namespace {
 
+struct CachedModel {
+    hana_model* dev = nullptr;
+    std::vector<float> a2v; /* what the device copy holds */
+};
+struct CachedTexture {
+    hana_texture* dev = nullptr;
+    const unsigned char* buffer = nullptr;
+    int w = 0, h = 0, bpp = 0;
+    unsigned long long fingerprint = 0;
+};
 struct DeviceCache {
     hana_ctx* ctx = nullptr;
-    std::map<Model*, hana_model*> models;
-    std::map<TGAImage*, hana_texture*> textures;
+    std::map<Model*, CachedModel> models;
+    std::map<TGAImage*, CachedTexture> textures;
     hana_rb* target = nullptr;
     hana_rb* shadow = nullptr;
     std::vector<float> a2v;
@@ -63,14 +73,32 @@ void copy_matrix(float* dst, const Matrix4x4& m) {
         for (int j = 0; j < 4; j++) dst[i * 4 + j] = m[i][j];
 }
 
+/* FNV-1a over 4096 evenly spaced bytes plus the last one: catches TGAImage flips, scale, clear and a reallocated image at
+ * the same address without reading megabytes per draw. An in-place edit of a few texels between two draws can escape it;
+ * hana_dropin_invalidate() (below) drops every cached texture for callers that paint into their textures. */
+unsigned long long fingerprint_of(const unsigned char* p, size_t n) {
+    unsigned long long h = 1469598103934665603ull;
+    const size_t step = n > 4096 ? n / 4096 : 1;
+    for (size_t i = 0; i < n; i += step) h = (h ^ p[i]) * 1099511628211ull;
+    if (n) h = (h ^ p[n - 1]) * 1099511628211ull;
+    return h;
+}
+
 hana_texture* texture_of(TGAImage* img) {
     if (!img || !img->buffer() || img->get_width() <= 0 || img->get_height() <= 0) return nullptr; /* fetches return 0 */
-    auto it = g.textures.find(img);
-    if (it != g.textures.end()) return it->second;
-    hana_texture* t = nullptr;
-    CK(hana_texture_upload(g.ctx, img->buffer(), img->get_width(), img->get_height(), img->get_bytespp(), &t));
-    g.textures[img] = t;
-    return t;
+    const int w = img->get_width(), h = img->get_height(), bpp = img->get_bytespp();
+    const unsigned long long fp = fingerprint_of(img->buffer(), (size_t)w * h * bpp);
+    CachedTexture& c = g.textures[img];
+    if (c.dev && c.buffer == img->buffer() && c.w == w && c.h == h && c.bpp == bpp && c.fingerprint == fp) return c.dev;
+    if (c.dev) hana_texture_destroy(c.dev); /* the image changed under the same TGAImage*: upload it again */
+    c.dev = nullptr;
+    CK(hana_texture_upload(g.ctx, img->buffer(), w, h, bpp, &c.dev));
+    c.buffer = img->buffer();
+    c.w = w;
+    c.h = h;
+    c.bpp = bpp;
+    c.fingerprint = fp;
+    return c.dev;
 }
 
 hana_rb* rb_of(hana_rb*& slot, int w, int h) {
@@ -85,6 +113,17 @@ hana_rb* rb_of(hana_rb*& slot, int w, int h) {
 }
 
 }  // namespace
+
+/* Drops every cached device texture and model (they are uploaded again at the next draw). For hosts that edit texels or
+ * vertices in place between draws in ways the cheap change detection above cannot see. */
+extern "C" void hana_dropin_invalidate(void) {
+    for (auto& kv : g.textures)
+        if (kv.second.dev) hana_texture_destroy(kv.second.dev);
+    g.textures.clear();
+    for (auto& kv : g.models)
+        if (kv.second.dev) hana_model_destroy(kv.second.dev);
+    g.models.clear();
+}
 
 void graphics_draw_triangle(DrawData* draw_data) {
     if (!g.ctx) {
@@ -113,15 +152,21 @@ void graphics_draw_triangle(DrawData* draw_data) {
             float* d = g.a2v.data() + ((size_t)i * 3 + j) * 8;
             d[0] = p.x; d[1] = p.y; d[2] = p.z; d[3] = n.x; d[4] = n.y; d[5] = n.z; d[6] = t.x; d[7] = t.y;
         }
-    hana_model*& dm = g.models[model];
-    if (dm && hana_model_ncorners(dm) != nfaces * 3) {
-        hana_model_destroy(dm);
-        dm = nullptr;
+    /* The gather above must run on every pass (the reference's normals change under it until they reach their fixed
+     * point); the upload only when the stream differs from what the device holds. */
+    CachedModel& cm = g.models[model];
+    if (cm.dev && hana_model_ncorners(cm.dev) != nfaces * 3) {
+        hana_model_destroy(cm.dev);
+        cm.dev = nullptr;
     }
-    if (!dm)
-        CK(hana_model_upload(g.ctx, g.a2v.data(), nfaces * 3, &dm));
-    else
-        CK(hana_model_update(dm, g.a2v.data(), nfaces * 3));
+    if (!cm.dev) {
+        CK(hana_model_upload(g.ctx, g.a2v.data(), nfaces * 3, &cm.dev));
+        cm.a2v = g.a2v;
+    } else if (cm.a2v.size() != g.a2v.size() || std::memcmp(cm.a2v.data(), g.a2v.data(), g.a2v.size() * sizeof(float)) != 0) {
+        CK(hana_model_update(cm.dev, g.a2v.data(), nfaces * 3));
+        cm.a2v = g.a2v;
+    }
+    hana_model* dm = cm.dev;
 
     HanaUniforms u;
     std::memset(&u, 0, sizeof(u));

@@ -294,6 +294,16 @@ HANA_API int hana_sweep_passes_ok(hana_sweep* s, int* ok);
 #define HANA_PRESENT_BGRA8 0
 #define HANA_PRESENT_BGR8 1
 HANA_API int hana_sweep_present(hana_sweep* s, int first, int count, int format, uint8_t* dst_host, void** dst_dev_out);
+/* Replaces TGAImage::write_tga_file(rle = true) (tgaimage.cpp:145-246, packets of unload_rle_data :206-246) for frames
+ * [first, first+count) of the sweep's last render: complete 24-bit RLE TGA files (header, packets, footer), byte-identical
+ * to the reference's writer and to hana_tga_write, produced on the device so that a frame leaves the GPU compressed.
+ *   hana_sweep_encode_tga  queues the encoder behind the render on the context's stream; reads nothing back.
+ *   hana_sweep_fetch_tga   waits for it, writes offsets[0..count] and sizes[0..count) (file f = dst_host[offsets[f],
+ *                          offsets[f] + sizes[f]); starts are 16-byte aligned, offsets[count] = bytes used) and copies the
+ *                          bytes to dst_host (pinned memory overlaps the next batch) on the copy stream: complete after
+ *                          hana_sync(). HANA_E_OVERFLOW if dst_capacity is too small. */
+HANA_API int hana_sweep_encode_tga(hana_sweep* s, int first, int count);
+HANA_API int hana_sweep_fetch_tga(hana_sweep* s, uint8_t* dst_host, size_t dst_capacity, uint64_t* offsets, uint64_t* sizes);
 /* Replaces TGAImage::write_tga_file (tgaimage.cpp:145-246): `data` = w*h*bytespp bytes in file order (top-left
  * origin is flagged); raw or RLE; byte-identical files. */
 HANA_API int hana_tga_write(const char* path, const uint8_t* data, int w, int h, int bytespp, int rle);
