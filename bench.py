@@ -424,91 +424,93 @@ def main():
         sweep = ctx.sweep(W, H, F)
 
     # ---- e2e: host uniforms in (pinned), every frame out (pinned), inside the timed region; two rings alternate so that
-    # the copies of batch k (copy stream) overlap the kernels of batch k+1. At most 128 frames per submission: bounds the
-    # pinned host memory per rank (8 ranks share one host).
+    # the copies of batch k (copy stream) overlap the kernels of batch k+1. The raw legs submit at most 128 frames at a
+    # time (bounds the pinned host memory per rank: 8 ranks share one host); the TGA leg, whose frames are ~7x smaller,
+    # up to 512.
     npx = W * H
     FE = min(F, 128)
-    sweep_b = ctx.sweep(W, H, FE)
+    FT = min(F, 512)
+    sweep_b = ctx.sweep(W, H, FT)
     rings = (sweep, sweep_b)
-    e2e_steps = args.steps * max(1, F // FE)  # the same number of frames as the value loop
 
-    def render_host(sw):
-        ck(ctx.L.hana_sweep_render(sw.h, model.h, hana.BLINN, C.c_void_p(pinned_u.ptr), FE, dtex.h, ntex.h, clr, float(hana.FLT_MAX)))
+    def render_host(sw, nf):
+        ck(ctx.L.hana_sweep_render(sw.h, model.h, hana.BLINN, C.c_void_p(pinned_u.ptr), nf, dtex.h, ntex.h, clr, float(hana.FLT_MAX)))
 
-    def run_e2e(step_fn, flush_fn=None):
+    def run_e2e(step_fn, nf, flush_fn=None):
+        steps_ = args.steps * max(1, F // nf)  # the same number of frames as the value loop
         for s in range(2):
             step_fn(s)
         if flush_fn:
-            flush_fn(2)
+            flush_fn()
         barrier()
         ctx.timer_start()
-        for s in range(e2e_steps):
+        for s in range(steps_):
             step_fn(s)
         if flush_fn:
-            flush_fn(e2e_steps)
+            flush_fn()
         ms_ = ctx.timer_stop()  # waits for every render and every copy
         barrier()
-        return FE * e2e_steps * world / (max_over_ranks(ms_) * 1e-3)
+        return nf * steps_ * world / (max_over_ranks(ms_) * 1e-3), steps_
 
     # (a) raw RGBA8 colour planes, what DrawModel::draw's caller reads (win32.cpp:361)
     pin_c = (PinnedBuffer(npx * 4 * FE), PinnedBuffer(npx * 4 * FE))
 
     def step_rgba(s):
-        render_host(rings[s & 1])
+        render_host(rings[s & 1], FE)
         rings[s & 1].download_async(0, FE, pin_c[s & 1].ptr, None)
 
-    e2e_rgba = run_e2e(step_rgba)
-    rgba_ok = int(np.frombuffer(pin_c[(e2e_steps - 1) & 1].array, np.uint8, count=npx * 4).max() > 1)
+    e2e_rgba, raw_steps = run_e2e(step_rgba, FE)
+    rgba_ok = int(np.frombuffer(pin_c[(raw_steps - 1) & 1].array, np.uint8, count=npx * 4).max() > 1)
     for b in pin_c:
         b.close()
     # (b) the surface window_draw_buffer builds (win32.cpp:348-370): flipped, B,G,R, 3 bytes per pixel, converted on the device
     pin_p = (PinnedBuffer(npx * 3 * FE), PinnedBuffer(npx * 3 * FE))
 
     def step_bgr(s):
-        render_host(rings[s & 1])
+        render_host(rings[s & 1], FE)
         ck(ctx.L.hana_sweep_present(rings[s & 1].h, 0, FE, hana.PRESENT_BGR8, C.c_void_p(pin_p[s & 1].ptr), None))
 
-    e2e_bgr = run_e2e(step_bgr)
-    # (c) RLE TGA files (tgaimage.cpp:206-246 packets, byte-identical to hana_tga_write), packetised on the device
-    e2e_tga, tga_info = None, None
-    if hasattr(ctx.L, "hana_sweep_encode_tga"):
-        cap = npx * 3 * FE  # the pinned ring is as large as the raw surfaces; an RLE file of these frames is ~5x smaller
-        offs = ((C.c_uint64 * (FE + 1))(), (C.c_uint64 * (FE + 1))())
-
-        szs = ((C.c_uint64 * FE)(), (C.c_uint64 * FE)())
-        state = {"pending": None}
-
-        def fetch(r):
-            ck(ctx.L.hana_sweep_fetch_tga(rings[r].h, C.c_void_p(pin_p[r].ptr), C.c_size_t(cap), offs[r], szs[r]))
-
-        def step_tga(s):
-            # render + encode batch s, then hand batch s-1 (the other ring, long finished) to the copy engine: the host never
-            # waits for the batch it has just queued
-            sw = rings[s & 1]
-            render_host(sw)
-            ck(ctx.L.hana_sweep_encode_tga(sw.h, 0, FE))
-            if state["pending"] is not None:
-                fetch(state["pending"])
-            state["pending"] = s & 1
-
-        def flush_tga(_n):
-            if state["pending"] is not None:
-                fetch(state["pending"])
-                state["pending"] = None
-
-        e2e_tga = run_e2e(step_tga, flush_tga)
-        last = (e2e_steps - 1) & 1
-        total_bytes = int(offs[last][FE])
-        # byte-identity of one delivered file with the host writer (outside the timed region)
-        import tempfile
-        f0 = bytes(pin_p[last].array[int(offs[last][0]):int(offs[last][0]) + int(szs[last][0])])
-        gcol, _ = rings[last].download(0)
-        with tempfile.TemporaryDirectory() as td:
-            pth = os.path.join(td, "f.tga")
-            hana.tga_write(pth, np.ascontiguousarray(gcol[::-1, :, 2::-1]), rle=True)
-            same = open(pth, "rb").read() == f0
-        tga_info = {"bytes_per_frame": total_bytes / FE, "file0_identical_to_hana_tga_write": bool(same)}
+    e2e_bgr, _ = run_e2e(step_bgr, FE)
     for b in pin_p:
+        b.close()
+    # (c) RLE TGA files (tgaimage.cpp:206-246 packets, byte-identical to hana_tga_write), packetised on the device
+    cap = FT * (1 << 21)  # 2 MiB of pinned ring per frame; an RLE file of these frames is ~1.2 MB (raw B,G,R: 6.2 MB)
+    pin_t = (PinnedBuffer(cap), PinnedBuffer(cap))
+    offs = ((C.c_uint64 * (FT + 1))(), (C.c_uint64 * (FT + 1))())
+    szs = ((C.c_uint64 * FT)(), (C.c_uint64 * FT)())
+    state = {"pending": None}
+
+    def fetch(r):
+        ck(ctx.L.hana_sweep_fetch_tga(rings[r].h, C.c_void_p(pin_t[r].ptr), C.c_size_t(cap), offs[r], szs[r]))
+
+    def step_tga(s):
+        # render + encode batch s, then hand batch s-1 (the other ring, long finished) to the copy engine: the host never
+        # waits for the batch it has just queued
+        sw = rings[s & 1]
+        render_host(sw, FT)
+        ck(ctx.L.hana_sweep_encode_tga(sw.h, 0, FT))
+        if state["pending"] is not None:
+            fetch(state["pending"])
+        state["pending"] = s & 1
+
+    def flush_tga():
+        if state["pending"] is not None:
+            fetch(state["pending"])
+            state["pending"] = None
+
+    e2e_tga, tga_steps = run_e2e(step_tga, FT, flush_tga)
+    last = (tga_steps - 1) & 1
+    total_bytes = int(offs[last][FT])
+    # byte-identity of one delivered file with the host writer (outside the timed region)
+    import tempfile
+    f0 = bytes(pin_t[last].array[int(offs[last][0]):int(offs[last][0]) + int(szs[last][0])])
+    gcol, _ = rings[last].download(0)
+    with tempfile.TemporaryDirectory() as td:
+        pth = os.path.join(td, "f.tga")
+        hana.tga_write(pth, np.ascontiguousarray(gcol[::-1, :, 2::-1]), rle=True)
+        same = open(pth, "rb").read() == f0
+    tga_info = {"bytes_per_frame": total_bytes / FT, "file0_identical_to_hana_tga_write": bool(same), "steps": tga_steps}
+    for b in pin_t:
         b.close()
 
     if rank == 0:
@@ -540,14 +542,14 @@ def main():
         kernel_ms = {k: v[0] for k, v in prof.items()}
         traffic = raster_main_traffic()
         if e2e_tga is not None:
-            e2e = {"value": e2e_tga, "unit": "frames/s", "frames_per_step": FE, "steps": e2e_steps, "h2d_bytes_per_step": usz * FE,
-                   "d2h_bytes_per_step": tga_info["bytes_per_frame"] * FE + 8 * (FE + 1), "delivered": "RLE TGA files",
+            e2e = {"value": e2e_tga, "unit": "frames/s", "frames_per_step": FT, "steps": tga_info["steps"], "h2d_bytes_per_step": usz * FT,
+                   "d2h_bytes_per_step": tga_info["bytes_per_frame"] * FT + 16 * FT + 8, "delivered": "RLE TGA files",
                    "file0_identical_to_hana_tga_write": tga_info["file0_identical_to_hana_tga_write"],
                    "note": "hana_sweep_render from pinned host uniforms; every frame comes back to pinned host memory as the "
                            "RLE-compressed 24-bit TGA file TGAImage::write_tga_file(rle=true) would write (tgaimage.cpp:145-246), "
                            "packetised on the device (hana_sweep_encode_tga), two rings so copies overlap the next batch"}
         else:
-            e2e = {"value": e2e_bgr, "unit": "frames/s", "frames_per_step": FE, "steps": e2e_steps, "h2d_bytes_per_step": usz * FE,
+            e2e = {"value": e2e_bgr, "unit": "frames/s", "frames_per_step": FE, "steps": raw_steps, "h2d_bytes_per_step": usz * FE,
                    "d2h_bytes_per_step": npx * 3 * FE, "delivered": "top-down B,G,R surfaces (hana_sweep_present)"}
         line = {
             "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -562,9 +564,9 @@ def main():
             "overflow_batches": overflow_total,
             "weak": weak,
             "e2e": e2e,
-            "e2e_rgba8": {"value": e2e_rgba, "unit": "frames/s", "d2h_bytes_per_step": npx * 4 * FE, "something_drawn": rgba_ok,
+            "e2e_rgba8": {"value": e2e_rgba, "unit": "frames/s", "frames_per_step": FE, "d2h_bytes_per_step": npx * 4 * FE, "something_drawn": rgba_ok,
                           "note": "same loop, raw RGBA8 colour planes (what DrawModel::draw's caller reads, win32.cpp:361); PCIe-bound"},
-            "e2e_bgr8": {"value": e2e_bgr, "unit": "frames/s", "d2h_bytes_per_step": npx * 3 * FE,
+            "e2e_bgr8": {"value": e2e_bgr, "unit": "frames/s", "frames_per_step": FE, "d2h_bytes_per_step": npx * 3 * FE,
                          "note": "same loop, top-down B,G,R surfaces made by present_kernel (hana_sweep_present)"},
             "gpu_launches": int(launches),
             "clocks": clk,

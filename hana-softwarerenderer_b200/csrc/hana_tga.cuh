@@ -33,7 +33,7 @@ constexpr int TGA_PPT = 16;                         /* pixels per thread */
 constexpr int TGA_CHUNK = TGA_THREADS * TGA_PPT;    /* pixels per CTA */
 constexpr int TGA_HEADER = 18, TGA_FOOTER = 26;
 #ifndef TGA_MIN_CTAS
-#define TGA_MIN_CTAS 4 /* resident CTAs per SM the encoder is compiled for: the phases of a CTA are separated by barriers, other CTAs fill the gaps */
+#define TGA_MIN_CTAS 6 /* resident CTAs per SM the encoder is compiled for: the phases of a CTA are separated by barriers, other CTAs fill the gaps */
 #endif
 
 struct alignas(16) TgaCarry { /* per frame: what chunk c hands to chunk c+1, in two instalments of one 16-byte word each */
