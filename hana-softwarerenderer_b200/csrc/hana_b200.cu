@@ -60,8 +60,10 @@ struct Scratch {
     size_t attr_total = 0;
     uint32_t* tri_count = nullptr; /* [frames][TRI_COUNT_WAYS] emitted triangles, then [frames] extra slots */
     size_t frames_cap = 0;
-    uint32_t* tile_arrays = nullptr; /* count | cursor | offset, each n_frames * n_tiles */
+    uint32_t* tile_arrays = nullptr; /* count | cursor | micro | offset, each n_frames * n_tiles (the first three padded) */
     size_t tile_arr_cap = 0;
+    unsigned long long* vis = nullptr; /* visibility buffer of the micro-triangle path (dense meshes only): n_frames * W * H */
+    size_t vis_cap = 0;
     float4* tile_recs = nullptr; /* pool of raster records: 4 float4 each */
     size_t pool_cap = 0;         /* float4 elements */
     uint4* work = nullptr;
@@ -104,7 +106,7 @@ struct hana_ctx {
     hana_sweep* host_sweep = nullptr;
     hana_rb* host_frame = nullptr;
     hana_rb* host_shadow = nullptr;
-    int occ[HANA_SHADER_COUNT][N_RASTER_MODES];
+    int occ[HANA_SHADER_COUNT][2 * N_RASTER_MODES]; /* [mode] without, [N_RASTER_MODES + mode] with a visibility buffer */
     uint32_t r8_slot_limit = R8_SLOT_LIMIT; /* HANA_R8_SLOT_LIMIT in the environment lowers it (tests force the WIDE variant) */
     uint64_t wide_r8_launches = 0;
 };
@@ -303,7 +305,7 @@ extern "C" int hana_ctx_destroy(hana_ctx* ctx) {
     for (Scratch* sp : {&ctx->sc, &ctx->sc2}) {
         Scratch& s = *sp;
         cudaFree(s.tri_rec); cudaFree(s.tri_attr); cudaFree(s.tri_count); cudaFree(s.tile_arrays);
-        cudaFree(s.tile_recs); cudaFree(s.work); cudaFree(s.counters); cudaFreeHost(s.counters_host);
+        cudaFree(s.tile_recs); cudaFree(s.work); cudaFree(s.counters); cudaFreeHost(s.counters_host); cudaFree(s.vis);
     }
     cudaStreamDestroy(ctx->side_stream);
     cudaEventDestroy(ctx->ev_fork); cudaEventDestroy(ctx->ev_join);
@@ -690,15 +692,15 @@ static int grow(T** ptr, size_t* cap, size_t need, hana_ctx* ctx) {
     return HANA_OK;
 }
 
-template <int MODE>
+template <int MODE, bool VIS>
 static int launch_raster(cudaStream_t st, int shader, int blocks, const RasterParams& rp, const CUtensorMap& a,
                          const CUtensorMap& b, const CUtensorMap& c) {
     if constexpr (mode_is_r8(MODE)) { /* the 1-byte maps take the ShadowShader only */
-        raster_kernel<HANA_SHADER_SHADOW, MODE><<<blocks, RW_THREADS, 0, st>>>(rp, a, b, c);
+        raster_kernel<HANA_SHADER_SHADOW, MODE, VIS><<<blocks, RW_THREADS, 0, st>>>(rp, a, b, c);
         return HANA_OK;
     }
 #define HANA_RASTER_CASE(S) \
-    case S: if constexpr (!mode_is_r8(MODE)) raster_kernel<S, MODE><<<blocks, RW_THREADS, 0, st>>>(rp, a, b, c); break;
+    case S: if constexpr (!mode_is_r8(MODE)) raster_kernel<S, MODE, VIS><<<blocks, RW_THREADS, 0, st>>>(rp, a, b, c); break;
     switch (shader) {
         HANA_RASTER_CASE(HANA_SHADER_SHADOW)
         HANA_RASTER_CASE(HANA_SHADER_BLINN)
@@ -713,15 +715,15 @@ static int launch_raster(cudaStream_t st, int shader, int blocks, const RasterPa
     return HANA_OK;
 }
 
-template <int MODE>
+template <int MODE, bool VIS>
 static int raster_occupancy(int shader) {
     int occ = 0;
     if constexpr (mode_is_r8(MODE)) {
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, raster_kernel<HANA_SHADER_SHADOW, MODE>, RW_THREADS, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, raster_kernel<HANA_SHADER_SHADOW, MODE, VIS>, RW_THREADS, 0);
         return occ;
     }
 #define HANA_OCC_CASE(S) \
-    case S: if constexpr (!mode_is_r8(MODE)) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, raster_kernel<S, MODE>, RW_THREADS, 0); break;
+    case S: if constexpr (!mode_is_r8(MODE)) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, raster_kernel<S, MODE, VIS>, RW_THREADS, 0); break;
     switch (shader) {
         HANA_OCC_CASE(HANA_SHADER_SHADOW)
         HANA_OCC_CASE(HANA_SHADER_BLINN)
@@ -773,7 +775,12 @@ static int run_pass(hana_ctx* ctx, const PassDesc& d) {
         HANA_TRY(grow(&sc.tri_count, &sc.frames_cap, (size_t)d.n_frames * (TRI_COUNT_WAYS + 1), ctx));
         const int tile_rows = (int)((n_tiles + 31) / 32);
         const size_t tiles_pad_total = (size_t)tile_rows * 32 * d.n_frames;
-        HANA_TRY(grow(&sc.tile_arrays, &sc.tile_arr_cap, tiles_pad_total * 2 + tiles_total, ctx));
+        HANA_TRY(grow(&sc.tile_arrays, &sc.tile_arr_cap, tiles_pad_total * 3 + tiles_total, ctx));
+        /* Dense meshes (at least one face per 16 pixels: BASELINE.json configs[3] has 1.2 per pixel) resolve their micro-
+         * triangles through a per-pixel visibility buffer instead of the tile lists (setup_kernel). Not for RenderBuffer
+         * draws: the target's existing depth takes part there. */
+        const bool use_vis = d.mode != MODE_RMW && !d.setup_only && (size_t)nfaces * 16 >= (size_t)d.W * d.H && !getenv("HANA_NO_VIS");
+        if (use_vis) HANA_TRY(grow(&sc.vis, &sc.vis_cap, (size_t)d.W * d.H * d.n_frames, ctx));
         HANA_TRY(grow(&sc.work, &sc.work_cap, tiles_total, ctx));
         if (!sc.tile_recs) HANA_TRY(grow(&sc.tile_recs, &sc.pool_cap, std::max<size_t>(tri_total * 2, 65536) * 4, ctx));
 
@@ -796,7 +803,9 @@ static int run_pass(hana_ctx* ctx, const PassDesc& d) {
         p.tri_extra = sc.tri_count + (size_t)d.n_frames * TRI_COUNT_WAYS;
         p.tile_count = sc.tile_arrays;
         p.tile_cursor = sc.tile_arrays + tiles_pad_total;
-        p.tile_offset = sc.tile_arrays + 2 * tiles_pad_total;
+        p.tile_micro = sc.tile_arrays + 2 * tiles_pad_total;
+        p.tile_offset = sc.tile_arrays + 3 * tiles_pad_total;
+        p.vis = use_vis ? sc.vis : nullptr;
         p.tile_rows = tile_rows;
         p.tile_pad = tile_rows * 32;
         p.tile_recs = sc.tile_recs;
@@ -809,7 +818,8 @@ static int run_pass(hana_ctx* ctx, const PassDesc& d) {
         /* zero: counters, per-frame triangle counts, tile counts + cursors (contiguous) */
         CU_TRY(cudaMemsetAsync(sc.counters, 0, sizeof(PassCounters), st));
         CU_TRY(cudaMemsetAsync(sc.tri_count, 0, sizeof(uint32_t) * d.n_frames * (TRI_COUNT_WAYS + 1), st));
-        CU_TRY(cudaMemsetAsync(sc.tile_arrays, 0, sizeof(uint32_t) * 2 * tiles_pad_total, st));
+        CU_TRY(cudaMemsetAsync(sc.tile_arrays, 0, sizeof(uint32_t) * 3 * tiles_pad_total, st));
+        if (use_vis) CU_TRY(cudaMemsetAsync(sc.vis, 0xFF, sizeof(unsigned long long) * (size_t)d.W * d.H * d.n_frames, st));
 
         cudaEvent_t ea, eb;
         if (nfaces > 0) {
@@ -934,12 +944,15 @@ static int run_pass(hana_ctx* ctx, const PassDesc& d) {
     /* MODE_SHADOW_R8 packs {shadow byte << 24 | triangle slot}: a pass that may emit more triangles per frame than 24 bits
      * address takes the WIDE variant (hana_kernels.cuh; ctx->r8_slot_limit is R8_SLOT_LIMIT unless a test lowered it) */
     const int mode = (d.mode == MODE_SHADOW_R8 && p.tri_cap > ctx->r8_slot_limit) ? (int)MODE_SHADOW_R8_WIDE : d.mode;
-    int& occ = ctx->occ[d.shader][mode];
+    const bool vis = p.vis != nullptr; /* never with MODE_RMW */
+    int& occ = ctx->occ[d.shader][mode + (vis ? N_RASTER_MODES : 0)];
     if (occ == 0) {
-        occ = mode == MODE_CLEAR_FOLD  ? raster_occupancy<MODE_CLEAR_FOLD>(d.shader)
-              : mode == MODE_RMW       ? raster_occupancy<MODE_RMW>(d.shader)
-              : mode == MODE_SHADOW_R8 ? raster_occupancy<MODE_SHADOW_R8>(HANA_SHADER_SHADOW)
-                                       : raster_occupancy<MODE_SHADOW_R8_WIDE>(HANA_SHADER_SHADOW);
+        occ = mode == MODE_RMW          ? raster_occupancy<MODE_RMW, false>(d.shader)
+              : mode == MODE_CLEAR_FOLD ? (vis ? raster_occupancy<MODE_CLEAR_FOLD, true>(d.shader) : raster_occupancy<MODE_CLEAR_FOLD, false>(d.shader))
+              : mode == MODE_SHADOW_R8  ? (vis ? raster_occupancy<MODE_SHADOW_R8, true>(HANA_SHADER_SHADOW)
+                                               : raster_occupancy<MODE_SHADOW_R8, false>(HANA_SHADER_SHADOW))
+                                        : (vis ? raster_occupancy<MODE_SHADOW_R8_WIDE, true>(HANA_SHADER_SHADOW)
+                                               : raster_occupancy<MODE_SHADOW_R8_WIDE, false>(HANA_SHADER_SHADOW));
         cudaGetLastError();
         if (occ <= 0) occ = 1;
     }
@@ -951,10 +964,13 @@ static int run_pass(hana_ctx* ctx, const PassDesc& d) {
     const CUtensorMap& tb = d.tm_depth ? *d.tm_depth : dummy;
     const CUtensorMap& tc = d.tm_r8 ? *d.tm_r8 : dummy;
     prof_begin(ctx, d.prof_kind, &ea, &eb, st);
-    int r = mode == MODE_CLEAR_FOLD  ? launch_raster<MODE_CLEAR_FOLD>(st, d.shader, blocks, rp, ta, tb, tc)
-            : mode == MODE_RMW       ? launch_raster<MODE_RMW>(st, d.shader, blocks, rp, ta, tb, tc)
-            : mode == MODE_SHADOW_R8 ? launch_raster<MODE_SHADOW_R8>(st, HANA_SHADER_SHADOW, blocks, rp, ta, tb, tc)
-                                     : launch_raster<MODE_SHADOW_R8_WIDE>(st, HANA_SHADER_SHADOW, blocks, rp, ta, tb, tc);
+    int r = mode == MODE_RMW          ? launch_raster<MODE_RMW, false>(st, d.shader, blocks, rp, ta, tb, tc)
+            : mode == MODE_CLEAR_FOLD ? (vis ? launch_raster<MODE_CLEAR_FOLD, true>(st, d.shader, blocks, rp, ta, tb, tc)
+                                             : launch_raster<MODE_CLEAR_FOLD, false>(st, d.shader, blocks, rp, ta, tb, tc))
+            : mode == MODE_SHADOW_R8  ? (vis ? launch_raster<MODE_SHADOW_R8, true>(st, HANA_SHADER_SHADOW, blocks, rp, ta, tb, tc)
+                                             : launch_raster<MODE_SHADOW_R8, false>(st, HANA_SHADER_SHADOW, blocks, rp, ta, tb, tc))
+                                      : (vis ? launch_raster<MODE_SHADOW_R8_WIDE, true>(st, HANA_SHADER_SHADOW, blocks, rp, ta, tb, tc)
+                                             : launch_raster<MODE_SHADOW_R8_WIDE, false>(st, HANA_SHADER_SHADOW, blocks, rp, ta, tb, tc));
     if (mode == MODE_SHADOW_R8_WIDE) ctx->wide_r8_launches++;
     prof_end(ctx, d.prof_kind, ea, eb, st);
     HANA_TRY(r);

@@ -39,6 +39,10 @@ constexpr int TILE_BITS = 20;        /* work item = frame << 20 | tile_y << 10 |
 constexpr uint32_t TILE_MASK = (1u << TILE_BITS) - 1u;
 constexpr uint32_t WORK_INVALID = 0xFFFFFFFFu;
 constexpr int SETUP_THREADS = 256;
+#ifndef HANA_MICRO_EXTENT
+#define HANA_MICRO_EXTENT 3
+#endif
+constexpr int MICRO_EXTENT = HANA_MICRO_EXTENT; /* a triangle whose pixel range is at most this many pixels on a side takes the visibility-buffer path */
 constexpr int TRI_COUNT_WAYS = 32;   /* per-frame statistics counters: one atomic per warp, spread so that they do not queue on one address */
 constexpr uint32_t DEAD_BBY = 0x0000FFFFu; /* bby of a slot that holds no triangle (y0 = 0xFFFF > y1 = 0: an empty range for every consumer) */
 constexpr int SCAN_THREADS = 1024;
@@ -91,6 +95,9 @@ struct PassParams {
     uint32_t* tile_count; /* [n_frames][tile_pad], indexed through tile_slot(): see there */
     uint32_t* tile_offset; /* [n_frames][n_tiles] */
     uint32_t* tile_cursor; /* [n_frames][tile_pad], tile_slot() */
+    uint32_t* tile_micro;  /* [n_frames][tile_pad], tile_slot(): != 0 where the visibility buffer holds fragments of the tile */
+    unsigned long long* vis; /* optional [n_frames][H][W]: (depth bits << 32 | ~order key) of the best micro-triangle fragment
+                                per pixel, all ones where there is none (dense meshes: see setup_kernel) */
     int tile_pad, tile_rows; /* tile_pad = 32 * tile_rows >= n_tiles */
     float4* tile_recs;    /* pool of raster records (4 x float4 each), grouped per (frame, tile) */
     uint32_t pool_cap;    /* in records */
@@ -315,7 +322,33 @@ __global__ void __launch_bounds__(SETUP_THREADS, 3) setup_kernel(const __grid_co
     if (face < p.nfaces && (uint32_t)face < p.tri_cap) {
         if (emit) {
             store_triangle<SHADER>(p, f, (uint32_t)face, r, v, v + V2F_N, v + 2 * V2F_N);
-            key = single_tile_slot(p, r);
+            /* Micro-triangles (pixel range at most 3x3: a dense mesh has millions, BASELINE.json configs[3]) do not go
+             * through the tile lists, where the tile's warp would walk them one by one. Their <= 9 pixels are tested right
+             * here with the scalar statement of the coverage / weight / depth arithmetic (hana_core.cuh: the bits the tile
+             * rasteriser's packed form produces) and resolved with one 64-bit atomicMin per covered pixel on the
+             * visibility buffer: smallest depth first, then the largest order key (graphics.cpp:359 in submission order).
+             * The tile rasteriser starts from that buffer and recomputes the winner's weights when it shades. */
+            const int x0 = (int)(r.bbx & 0xFFFFu), x1 = (int)(r.bbx >> 16), y0 = (int)(r.bby & 0xFFFFu), y1 = (int)(r.bby >> 16);
+            if (p.vis && x1 - x0 < MICRO_EXTENT && y1 - y0 < MICRO_EXTENT && r.uz < 0.f) {
+                for (int y = y0; y <= y1; y++) {
+                    if ((y >> 4) < p.band_y0 || (y >> 4) >= p.band_y1) continue;
+                    for (int x = x0; x <= x1; x++) {
+                        float ux, uy, su;
+                        if (!coverage_test(r.ax, r.ay, r.s0x, r.s0y, r.s1x, r.s1y, r.uz, r.thr, (float)x, (float)y, ux, uy, su)) continue;
+                        float w0, w1, w2;
+                        barycentric_weights(ux, uy, su, r.uz, r.ruz, w0, w1, w2);
+                        const float z = interpolate_depth(r.d0, r.d1, r.d2, w0, w1, w2);
+                        if (!(z == z)) continue; /* a NaN depth never wins */
+                        atomicMin(p.vis + ((size_t)f * p.H + y) * p.W + x,
+                                  ((unsigned long long)__float_as_uint(z) << 32) | (unsigned long long)(0xFFFFFFFFu - r.key));
+                        p.tile_micro[(size_t)f * p.tile_pad + tile_slot(p, (y >> 4) * p.tiles_x + (x >> 4))] = 1u;
+                    }
+                }
+                /* not listed: the pair kernels skip a record whose pixel range is empty */
+                reinterpret_cast<float*>(p.tri_rec + ((size_t)f * p.tri_cap + (uint32_t)face) * 4 + 2)[1] = __uint_as_float(DEAD_BBY);
+            } else {
+                key = single_tile_slot(p, r);
+            }
         } else {
             p.tri_rec[((size_t)f * p.tri_cap + (uint32_t)face) * 4 + 2] = make_float4(0.f, __uint_as_float(DEAD_BBY), 0.f, 0.f);
         }
@@ -363,11 +396,15 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_kernel(PassParams p) {
     const int f = blockIdx.y;
     const int t0 = blockIdx.x * SCAN_CHUNK + (int)threadIdx.x * 4;
     const uint32_t* tc = p.tile_count + (size_t)f * p.tile_pad;
-    uint32_t c[4];
+    const uint32_t* tm = p.tile_micro + (size_t)f * p.tile_pad;
+    uint32_t c[4], m[4];
 #pragma unroll
-    for (int k = 0; k < 4; k++) c[k] = (t0 + k < p.n_tiles) ? tc[tile_slot(p, t0 + k)] : 0u;
+    for (int k = 0; k < 4; k++) {
+        c[k] = (t0 + k < p.n_tiles) ? tc[tile_slot(p, t0 + k)] : 0u;
+        m[k] = (p.vis && t0 + k < p.n_tiles) ? tm[tile_slot(p, t0 + k)] : 0u; /* the visibility buffer holds fragments of the tile */
+    }
     const uint32_t refs = c[0] + c[1] + c[2] + c[3];
-    const uint32_t ne = (c[0] != 0u) + (c[1] != 0u) + (c[2] != 0u) + (c[3] != 0u);
+    const uint32_t ne = ((c[0] | m[0]) != 0u) + ((c[1] | m[1]) != 0u) + ((c[2] | m[2]) != 0u) + ((c[3] | m[3]) != 0u);
     const uint32_t ex_refs = block_exclusive_scan(refs, &s_total_refs, warp_sums);
     const uint32_t ex_ne = block_exclusive_scan(ne, &s_total_ne, warp_sums);
     if (threadIdx.x == 0) {
@@ -390,9 +427,9 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_kernel(PassParams p) {
         const int t = t0 + k;
         if (t < p.n_tiles) {
             to[t] = off;
-            if (c[k]) {
+            if (c[k] | m[k]) {
                 const uint32_t tx = (uint32_t)(t % p.tiles_x), ty = (uint32_t)(t / p.tiles_x);
-                p.work[wi++] = make_uint4(((uint32_t)f << TILE_BITS) | (ty << 10) | tx, c[k], off, 0u);
+                p.work[wi++] = make_uint4(((uint32_t)f << TILE_BITS) | (ty << 10) | tx, c[k], off, m[k] ? 1u : 0u);
             }
             off += c[k];
         }
@@ -577,7 +614,10 @@ __device__ __forceinline__ void clear_item(const RasterParams& q, uint32_t item,
     if (ty < p.band_y0 || ty >= p.band_y1) return; /* warp-uniform */
     const int tx_l = gx * G + (int)lane;
     bool empty = false;
-    if ((int)lane < G && tx_l < p.tiles_x) empty = p.tile_count[(size_t)f * p.tile_pad + tile_slot(p, ty * p.tiles_x + tx_l)] == 0u;
+    if ((int)lane < G && tx_l < p.tiles_x) {
+        const size_t ts = (size_t)f * p.tile_pad + tile_slot(p, ty * p.tiles_x + tx_l);
+        empty = p.tile_count[ts] == 0u && (!p.vis || p.tile_micro[ts] == 0u);
+    }
     const unsigned mask = __ballot_sync(FULL, empty);
     if (!mask) return;
     if (mode_is_r8(MODE)) {
@@ -697,7 +737,9 @@ __device__ __forceinline__ uint32_t shade_fragment(const FragUniforms& fu, const
     return shade_fragment_t<SHADER, false>(fu, ap, w0, w1, w2, diffuse, normal, sh, safe, bad);
 }
 
-template <int SHADER, int MODE>
+/* VIS: the pass has a visibility buffer (micro-triangle path of dense meshes); a variant of its own so that the code and
+ * registers it takes stay out of the kernels every other pass runs */
+template <int SHADER, int MODE, bool VIS>
 __global__ void __launch_bounds__(RW_THREADS, ShaderAttrs<SHADER>::LIT ? HANA_OCC_LIT : HANA_OCC_OTHER)
     raster_kernel(const __grid_constant__ RasterParams q, const __grid_constant__ CUtensorMap tm_color, const __grid_constant__ CUtensorMap tm_depth,
                   const __grid_constant__ CUtensorMap tm_r8) {
@@ -749,6 +791,8 @@ __global__ void __launch_bounds__(RW_THREADS, ShaderAttrs<SHADER>::LIT ? HANA_OC
         if (cur.x == WORK_INVALID) break;
         cur.y = __shfl_sync(FULL, e_cur.y, 0);
         cur.z = __shfl_sync(FULL, e_cur.z, 0);
+        /* the tile has fragments in the visibility buffer (only passes that were given one: warp-uniform and false otherwise) */
+        const bool has_micro = VIS && MODE != MODE_RMW && __shfl_sync(FULL, e_cur.w, 0) != 0u;
         __syncwarp(); /* every lane is done with the previous tile's shared memory (fu, ord, tri) */
         uint4 e_nxt = make_uint4(WORK_INVALID, 0u, 0u, 0u);
         uint32_t i_nn = 0, clr_base = 0;
@@ -807,11 +851,28 @@ __global__ void __launch_bounds__(RW_THREADS, ShaderAttrs<SHADER>::LIT ? HANA_OC
             __syncwarp();
         }
 
+        /* Micro-triangles were resolved per pixel by setup_kernel: the resolve starts from their best fragment. Their slot is
+         * their face index (unclipped faces only), i.e. order key >> 3. */
+        const unsigned long long* vis_frame = has_micro ? p.vis + (size_t)f * p.H * p.W : nullptr;
+        if (has_micro) {
+#pragma unroll
+            for (int sb = 0; sb < 8; sb++) {
+                const int px = ipx0 + (sb & 1) * 8, py = ipy0 + (sb >> 1) * 4;
+                if (px < p.W && py < p.H) {
+                    const unsigned long long vv = __ldg(vis_frame + (size_t)py * p.W + px);
+                    if (vv != ~0ull) {
+                        bz[sb] = __uint_as_float((uint32_t)(vv >> 32));
+                        bj[sb] = (0xFFFFFFFFu - (uint32_t)vv) >> 3;
+                    }
+                }
+            }
+        }
+
         /* Equal depths (rare): graphics.cpp:359 is "skip if z > stored" in submission order, so a fragment as deep as the
          * target's value passes (LEQUAL) and of two equally deep fragments the later submission wins. */
         /* A tile whose whole list fits one chunk (the common case) parks the record's index in the chunk instead of the
          * triangle's slot in the frame: its staged record (order key) and staged attribute block are then one LDS away. */
-        const bool single = !INLOOP && cnt <= (uint32_t)RW_CHUNK; /* warp-uniform */
+        const bool single = !INLOOP && cnt <= (uint32_t)RW_CHUNK && !has_micro; /* warp-uniform; visibility-buffer winners are known by their slot in the frame */
         auto wins_tie = [&](const int sb, const uint32_t key) -> bool {
             if (bj[sb] == ORD_NONE) return true;
             const uint32_t kb = single ? __float_as_uint(wt.tri[bj[sb] * RW_REC_Q + 4].y)
@@ -982,6 +1043,30 @@ __global__ void __launch_bounds__(RW_THREADS, ShaderAttrs<SHADER>::LIT ? HANA_OC
             }
         }
 
+        /* which of the lane's pixels are still owned by a visibility-buffer fragment (no list record beat it): those have no
+         * parked weights / no ShadowShader byte yet. A micro-triangle is never listed, so the slot tells. */
+        uint32_t micro_mask = 0;
+        if (has_micro) {
+#pragma unroll
+            for (int sb = 0; sb < 8; sb++) {
+                const int px = ipx0 + (sb & 1) * 8, py = ipy0 + (sb >> 1) * 4;
+                if (px < p.W && py < p.H) {
+                    const unsigned long long vv = __ldg(vis_frame + (size_t)py * p.W + px);
+                    if (vv != ~0ull && bj[sb] != ORD_NONE && (bj[sb] & SLOT_MASK) == ((0xFFFFFFFFu - (uint32_t)vv) >> 3) &&
+                        (!INLOOP || WIDE || (bj[sb] >> 24) == 0u) && __float_as_uint(bz[sb]) == (uint32_t)(vv >> 32))
+                        micro_mask |= 1u << sb;
+                }
+            }
+        }
+        /* graphics.cpp:222-233 + :186-194 for one known-covered pixel of triangle `slot`, from its raster record: the scalar
+         * statement of what the record loop computes two pixels at a time */
+        auto micro_weights = [&](uint32_t slot, float fx, float fy, float& w0, float& w1, float& w2) {
+            const float4 q0 = __ldg(frame_rec + (size_t)slot * 4), q1 = __ldg(frame_rec + (size_t)slot * 4 + 1),
+                         q3 = __ldg(frame_rec + (size_t)slot * 4 + 3);
+            float ux, uy, su;
+            coverage_test(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, fx, fy, ux, uy, su);
+            barycentric_weights(ux, uy, su, q1.z, q3.w, w0, w1, w2);
+        };
         if (tma && mode_is_r8(MODE)) {
             if (lane == 0) tma_wait_read0(); /* the previous tile's store has drained the staging tile */
             __syncwarp();
@@ -991,7 +1076,15 @@ __global__ void __launch_bounds__(RW_THREADS, ShaderAttrs<SHADER>::LIT ? HANA_OC
 #pragma unroll
             for (int sb = 0; sb < 8; sb++) {
                 const int pix = pix0 + (sb >> 1) * 64 + (sb & 1) * 8;
-                const uint8_t v = WIDE ? (uint8_t)(bb[sb >> 2] >> (8 * (sb & 3))) : (uint8_t)(bj[sb] == ORD_NONE ? 0u : (bj[sb] >> 24));
+                uint8_t v = WIDE ? (uint8_t)(bb[sb >> 2] >> (8 * (sb & 3))) : (uint8_t)(bj[sb] == ORD_NONE ? 0u : (bj[sb] >> 24));
+                if (micro_mask & (1u << sb)) { /* ShadowShader::fragment IShader.cpp:176-180 for a visibility-buffer winner */
+                    const uint32_t slot = bj[sb] & SLOT_MASK;
+                    float w0, w1, w2;
+                    micro_weights(slot, (float)(ipx0 + (sb & 1) * 8), (float)(ipy0 + (sb >> 1) * 4), w0, w1, w2);
+                    const float4 rw = __ldg(frame_attr + (size_t)slot * 2), at = __ldg(frame_attr + (size_t)slot * 2 + 1);
+                    const VaryingWeights vw = varying_weights(w0, w1, w2, rw.x, rw.y, rw.z);
+                    v = (uint8_t)shadow_byte(interp(vw, at.x, at.y, at.z));
+                }
                 if (q.pixels_covered) covered_acc += __popc(__ballot_sync(FULL, bj[sb] != ORD_NONE));
                 if (tma) {
                     wt.r8[pix] = v;
@@ -1023,7 +1116,8 @@ __global__ void __launch_bounds__(RW_THREADS, ShaderAttrs<SHADER>::LIT ? HANA_OC
                 else if (in_frame && slot != ORD_NONE) col = q.color[(size_t)f * q.frame_stride + (size_t)py * p.W + px];
             }
             if (slot != ORD_NONE) {
-                const float w0 = pw0[pix], w1 = wt.pw1[pix], w2 = wt.pw2[pix];
+                float w0 = pw0[pix], w1 = wt.pw1[pix], w2 = wt.pw2[pix];
+                if (micro_mask & (1u << sb)) micro_weights(slot, (float)px, (float)py, w0, w1, w2); /* never parked: recompute */
                 uint32_t rgb;
                 if (single) rgb = shade_fragment<SHADER>(wt.fu, AttrShared{wt.sattr + slot * NQ}, w0, w1, w2, q.diffuse, q.normal, sh, frame_attr);
                 else rgb = shade_fragment<SHADER>(wt.fu, AttrGlobal{frame_attr + (size_t)slot * NQ}, w0, w1, w2, q.diffuse, q.normal, sh, frame_attr);
