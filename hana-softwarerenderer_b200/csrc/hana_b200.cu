@@ -56,8 +56,10 @@ enum ProfKind { PROF_BEGIN = 0, PROF_SETUP, PROF_SCAN, PROF_FILL, PROF_RASTER_SH
 struct Scratch {
     float4* tri_rec = nullptr; /* 4 float4 per record */
     float4* tri_attr = nullptr;
+    uint2* tri_bbox = nullptr;
     size_t tri_total = 0; /* records allocated (n_frames * tri_cap) */
     size_t attr_total = 0;
+    size_t bbox_total = 0;
     uint32_t* tri_count = nullptr; /* [frames][TRI_COUNT_WAYS] emitted triangles, then [frames] extra slots */
     size_t frames_cap = 0;
     uint32_t* tile_arrays = nullptr; /* count | cursor | micro | offset, each n_frames * n_tiles (the first three padded) */
@@ -304,7 +306,7 @@ extern "C" int hana_ctx_destroy(hana_ctx* ctx) {
     if (ctx->host_shadow) hana_rb_destroy(ctx->host_shadow);
     for (Scratch* sp : {&ctx->sc, &ctx->sc2}) {
         Scratch& s = *sp;
-        cudaFree(s.tri_rec); cudaFree(s.tri_attr); cudaFree(s.tri_count); cudaFree(s.tile_arrays);
+        cudaFree(s.tri_rec); cudaFree(s.tri_attr); cudaFree(s.tri_bbox); cudaFree(s.tri_count); cudaFree(s.tile_arrays);
         cudaFree(s.tile_recs); cudaFree(s.work); cudaFree(s.counters); cudaFreeHost(s.counters_host); cudaFree(s.vis);
     }
     cudaStreamDestroy(ctx->side_stream);
@@ -772,6 +774,7 @@ static int run_pass(hana_ctx* ctx, const PassDesc& d) {
         size_t tri_total = (size_t)tri_cap * d.n_frames;
         HANA_TRY(grow(&sc.tri_rec, &sc.tri_total, tri_total * 4, ctx));
         HANA_TRY(grow(&sc.tri_attr, &sc.attr_total, tri_total * MAX_ATTR_QUADS, ctx));
+        HANA_TRY(grow(&sc.tri_bbox, &sc.bbox_total, tri_total, ctx));
         HANA_TRY(grow(&sc.tri_count, &sc.frames_cap, (size_t)d.n_frames * (TRI_COUNT_WAYS + 1), ctx));
         const int tile_rows = (int)((n_tiles + 31) / 32);
         const size_t tiles_pad_total = (size_t)tile_rows * 32 * d.n_frames;
@@ -798,6 +801,7 @@ static int run_pass(hana_ctx* ctx, const PassDesc& d) {
         p.uniforms = d.uniforms;
         p.tri_rec = sc.tri_rec;
         p.tri_attr = sc.tri_attr;
+        p.tri_bbox = sc.tri_bbox;
         p.tri_cap = tri_cap;
         p.tri_count = sc.tri_count;
         p.tri_extra = sc.tri_count + (size_t)d.n_frames * TRI_COUNT_WAYS;
@@ -1884,12 +1888,12 @@ extern "C" int hana_stage_setup(hana_ctx* ctx, const hana_model* model, int shad
     }
     cudaFree(dbg);
     if (e != cudaSuccess) return fail(HANA_E_CUDA, cudaGetErrorString(e));
+    std::vector<uint2> bbs(nslots);
+    if (nslots && cudaMemcpy(bbs.data(), ctx->sc.tri_bbox, sizeof(uint2) * nslots, cudaMemcpyDeviceToHost) != cudaSuccess)
+        return fail(HANA_E_CUDA, "cudaMemcpy of the slot table failed");
     std::vector<uint32_t> idx;
-    for (uint32_t i = 0; i < nslots; i++) { /* slots of faces that emitted nothing carry the empty pixel range */
-        uint32_t bby;
-        memcpy(&bby, &recs[(size_t)i * 16 + 9], 4);
-        if (bby != DEAD_BBY) idx.push_back(i);
-    }
+    for (uint32_t i = 0; i < nslots; i++) /* slots of faces that emitted nothing carry the empty pixel range */
+        if (bbs[i].y != DEAD_BBY) idx.push_back(i);
     const uint32_t n = (uint32_t)idx.size();
     auto key_of = [&](uint32_t i) {
         uint32_t k;

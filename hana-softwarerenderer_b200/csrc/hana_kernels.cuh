@@ -89,6 +89,9 @@ struct PassParams {
     /* scratch */
     float4* tri_rec;      /* [n_frames][tri_cap][4]: raster records */
     float4* tri_attr;     /* [n_frames][tri_cap][attr_quads] */
+    uint2* tri_bbox;      /* [n_frames][tri_cap] pixel range (bbx, bby) of the slot's triangle as the PAIR kernels see it: DEAD_BBY
+                             in .y for a slot that is not to be listed (no triangle, or a micro-triangle). 8 bytes per slot
+                             instead of a 16-byte read out of every 64-byte record */
     uint32_t tri_cap;     /* slots per frame: slot = face index for an unclipped face, slots >= nfaces for what clipping emits */
     uint32_t* tri_count;  /* [n_frames][TRI_COUNT_WAYS] triangles emitted (statistics only; spread over several counters) */
     uint32_t* tri_extra;  /* [n_frames] slots allocated beyond nfaces by the clipped path */
@@ -213,6 +216,7 @@ __device__ __forceinline__ void store_triangle(const PassParams& p, int f, uint3
     dst[1] = make_float4(r.s1x, r.s1y, r.uz, r.thr);
     dst[2] = make_float4(__uint_as_float(r.bbx), __uint_as_float(r.bby), __uint_as_float(slot), __uint_as_float(r.key));
     dst[3] = make_float4(r.d0, r.d1, r.d2, r.ruz);
+    p.tri_bbox[(size_t)f * p.tri_cap + slot] = make_uint2(r.bbx, r.bby);
     float a[(NQ - 1) * 4];
 #pragma unroll
     for (int k = 0; k < NA; k++) {
@@ -345,12 +349,12 @@ __global__ void __launch_bounds__(SETUP_THREADS, 3) setup_kernel(const __grid_co
                     }
                 }
                 /* not listed: the pair kernels skip a record whose pixel range is empty */
-                reinterpret_cast<float*>(p.tri_rec + ((size_t)f * p.tri_cap + (uint32_t)face) * 4 + 2)[1] = __uint_as_float(DEAD_BBY);
+                p.tri_bbox[(size_t)f * p.tri_cap + (uint32_t)face] = make_uint2(0u, DEAD_BBY);
             } else {
                 key = single_tile_slot(p, r);
             }
         } else {
-            p.tri_rec[((size_t)f * p.tri_cap + (uint32_t)face) * 4 + 2] = make_float4(0.f, __uint_as_float(DEAD_BBY), 0.f, 0.f);
+            p.tri_bbox[(size_t)f * p.tri_cap + (uint32_t)face] = make_uint2(0u, DEAD_BBY);
         }
     }
     const unsigned live = __ballot_sync(0xFFFFFFFFu, emit);
@@ -457,8 +461,8 @@ __global__ void __launch_bounds__(256) pairs_kernel(PassParams p) {
     const float4* warp_rec = p.tri_rec + ((size_t)f * p.tri_cap + (i & ~31u)) * 4;
     int tx0 = 0, ty0 = 0, ntx = 1, nt = 0;
     if (i < n) {
-        const float4 q2 = __ldg(warp_rec + lane * 4 + 2);
-        const uint32_t bbx = __float_as_uint(q2.x), bby = __float_as_uint(q2.y);
+        const uint2 bb = __ldg(p.tri_bbox + (size_t)f * p.tri_cap + i);
+        const uint32_t bbx = bb.x, bby = bb.y;
         tx0 = (int)(bbx & 0xFFFFu) >> 4;
         ty0 = max((int)(bby & 0xFFFFu) >> 4, p.band_y0);
         ntx = ((int)(bbx >> 16) >> 4) - tx0 + 1;
