@@ -39,6 +39,9 @@ constexpr int TILE_BITS = 20;        /* work item = frame << 20 | tile_y << 10 |
 constexpr uint32_t TILE_MASK = (1u << TILE_BITS) - 1u;
 constexpr uint32_t WORK_INVALID = 0xFFFFFFFFu;
 constexpr int SETUP_THREADS = 256;
+#ifndef HANA_SETUP_CTAS
+#define HANA_SETUP_CTAS 3 /* resident CTAs per SM setup_kernel is compiled for */
+#endif
 #ifndef HANA_MICRO_EXTENT
 #define HANA_MICRO_EXTENT 3
 #endif
@@ -293,7 +296,7 @@ template <int SHADER>
 /* `p` is __grid_constant__: the rare clipped path takes its address (a __noinline__ call), and without the qualifier
  * every thread first copies all of PassParams to local memory. For the same reason the 39 vertex-stage floats are
  * copied to a second array only on that path, so the common path keeps them in registers. */
-__global__ void __launch_bounds__(SETUP_THREADS, 3) setup_kernel(const __grid_constant__ PassParams p) {
+__global__ void __launch_bounds__(SETUP_THREADS, HANA_SETUP_CTAS) setup_kernel(const __grid_constant__ PassParams p) {
     const int f = blockIdx.y;
     const int face = blockIdx.x * SETUP_THREADS + threadIdx.x;
     const unsigned lane = threadIdx.x & 31u;

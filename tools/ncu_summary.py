@@ -61,7 +61,7 @@ def main():
         ri, wi = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
         best = None
         for r in data:
-            if "raster_kernel<(int)1, (int)0>" in r[name_i]:
+            if "raster_kernel<1, 0" in r[name_i] or "raster_kernel<(int)1, (int)0" in r[name_i]:
                 best = r  # the last such launch (steady state)
         if best is None:
             raise SystemExit("no raster_kernel<BLINN, CLEAR_FOLD> launch in the report")
