@@ -534,6 +534,16 @@ extern "C" int hana_texture_destroy(hana_texture* t) {
 }
 
 /* ---- launches ------------------------------------------------------------------ */
+/* nbytes (a multiple of 4) from device memory to a cudaMallocHost allocation, by a kernel: see post_words_kernel */
+static int post_to_host(hana_ctx* ctx, void* dst_pinned, const void* src_dev, size_t nbytes, cudaStream_t st) {
+    const uint32_t n = (uint32_t)(nbytes / 4);
+    if (!n) return HANA_OK;
+    post_words_kernel<<<(unsigned)std::min<uint32_t>((n + 255) / 256, 64u), 256, 0, st>>>((uint32_t*)dst_pinned, (const uint32_t*)src_dev, n);
+    ctx->launches++;
+    CU_TRY(cudaGetLastError());
+    return HANA_OK;
+}
+
 static int launch_fill32(hana_ctx* ctx, uint32_t* dst, uint32_t value, size_t n) {
     if (n == 0) return HANA_OK;
     int blocks = (int)std::min<size_t>((n / 4 + 255) / 256 + 1, (size_t)ctx->sm_count * 16);
@@ -867,10 +877,9 @@ static int run_pass(hana_ctx* ctx, const PassDesc& d) {
             c.pool_used = 1;
             c.n_work = 0xFFFFFFFFu;
             if (d.counters_pinned)
-                CU_TRY(cudaMemcpyAsync(d.counters_pinned, sc.counters, sizeof(PassCounters), cudaMemcpyDeviceToHost, st));
+                HANA_TRY(post_to_host(ctx, d.counters_pinned, sc.counters, sizeof(PassCounters), st));
             if (d.tri_counts_pinned)
-                CU_TRY(cudaMemcpyAsync(d.tri_counts_pinned, sc.tri_count, sizeof(uint32_t) * d.n_frames * TRI_COUNT_WAYS,
-                                       cudaMemcpyDeviceToHost, st));
+                HANA_TRY(post_to_host(ctx, d.tri_counts_pinned, sc.tri_count, sizeof(uint32_t) * d.n_frames * TRI_COUNT_WAYS, st));
             if (d.tri_cap_used) *d.tri_cap_used = tri_cap;
             if (d.pool_cap_used) *d.pool_cap_used = p.pool_cap;
             lists_ready = true;
@@ -1403,7 +1412,7 @@ static int sweep_render_common(hana_sweep* s, const hana_model* model, int shade
     HANA_TRY(sweep_render_passes(s, model, shader_id, enable_shadow, n_frames, diffuse, normal, clear_rgba, clear_depth, true));
     const int slot = s->next_slot;
     s->next_slot = (slot + 1) % (hana_sweep::CHECK_RING + 1);
-    CU_TRY(cudaMemcpyAsync(&s->pin->need[slot], s->overflow, sizeof(OverflowRecord), cudaMemcpyDeviceToHost, ctx->stream));
+    HANA_TRY(post_to_host(ctx, &s->pin->need[slot], s->overflow, sizeof(OverflowRecord), ctx->stream));
     CU_TRY(cudaEventRecord(s->ev_check[slot], ctx->stream));
     CU_TRY(cudaEventRecord(s->ev_render, ctx->stream));
     hana_sweep::Pending& pd = s->pending;
@@ -1681,8 +1690,8 @@ static int tga_encode_launch(hana_sweep* s, int first, int count) {
     prof_end(ctx, PROF_OTHER, a, b);
     ctx->launches += 3;
     CU_TRY(cudaGetLastError());
-    CU_TRY(cudaMemcpyAsync(t.meta_pin, t.offsets, sizeof(unsigned long long) * (count + 1), cudaMemcpyDeviceToHost, ctx->stream));
-    CU_TRY(cudaMemcpyAsync(t.meta_pin + s->max_frames + 1, t.sizes, sizeof(unsigned long long) * count, cudaMemcpyDeviceToHost, ctx->stream));
+    HANA_TRY(post_to_host(ctx, t.meta_pin, t.offsets, sizeof(unsigned long long) * (count + 1), ctx->stream));
+    HANA_TRY(post_to_host(ctx, t.meta_pin + s->max_frames + 1, t.sizes, sizeof(unsigned long long) * count, ctx->stream));
     CU_TRY(cudaEventRecord(t.ev, ctx->stream));
     t.first = first;
     t.count = count;

@@ -1186,6 +1186,15 @@ __global__ void __launch_bounds__(RW_THREADS, ShaderAttrs<SHADER>::LIT ? HANA_OC
 }
 
 /* ---- helpers ---------------------------------------------------------------- */
+/* Small device -> pinned-host read-backs of the asynchronous sweep path (capacity needs, counters, file offsets) as a
+ * KERNEL that stores into the mapped host allocation. A cudaMemcpyAsync would do, but it is a copy-engine operation:
+ * queued behind a frame download of the previous batch in the engine's FIFO, it held up this stream's kernels until that
+ * download had finished (measured: 512-frame batches took render + encode + copy = 25.8 ms instead of max(16.5, 9.3)). */
+__global__ void post_words_kernel(uint32_t* __restrict__ dst_host, const uint32_t* __restrict__ src, uint32_t n) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) dst_host[i] = src[i];
+    __threadfence_system();
+}
+
 __global__ void fill32_kernel(uint32_t* __restrict__ dst, uint32_t value, size_t n) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     size_t stride = (size_t)gridDim.x * blockDim.x;
