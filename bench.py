@@ -513,6 +513,23 @@ def main():
     for b in pin_t:
         b.close()
 
+    # ---- the box's plain device->pinned-host copy rate with all N ranks copying at once: the ceiling of any e2e figure
+    d2h_bytes = 256 << 20
+    dsrc = torch.empty(d2h_bytes, dtype=torch.uint8, device="cuda")
+    hdst = torch.empty(d2h_bytes, dtype=torch.uint8).pin_memory()
+    for _ in range(2):
+        hdst.copy_(dsrc, non_blocking=True)
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(8):
+        hdst.copy_(dsrc, non_blocking=True)
+    ev1.record()
+    torch.cuda.synchronize()
+    d2h_ms = max_over_ranks(ev0.elapsed_time(ev1))
+    d2h_ceiling_gbs = 8 * d2h_bytes * world / (d2h_ms * 1e-3) / 1e9
+    del dsrc, hdst
+
     if rank == 0:
         if old_affinity:
             os.sched_setaffinity(0, old_affinity)  # the CPU legs below use every host core
@@ -544,6 +561,8 @@ def main():
         if e2e_tga is not None:
             e2e = {"value": e2e_tga, "unit": "frames/s", "frames_per_step": FT, "steps": tga_info["steps"], "h2d_bytes_per_step": usz * FT,
                    "d2h_bytes_per_step": tga_info["bytes_per_frame"] * FT + 16 * FT + 8, "delivered": "RLE TGA files",
+                   "d2h_gb_per_s": e2e_tga * tga_info["bytes_per_frame"] / 1e9, "d2h_ceiling_gb_per_s": d2h_ceiling_gbs,
+                   "d2h_ceiling_note": "plain pinned device->host copies by all %d ranks at once on this box" % world,
                    "file0_identical_to_hana_tga_write": tga_info["file0_identical_to_hana_tga_write"],
                    "note": "hana_sweep_render from pinned host uniforms; every frame comes back to pinned host memory as the "
                            "RLE-compressed 24-bit TGA file TGAImage::write_tga_file(rle=true) would write (tgaimage.cpp:145-246), "
@@ -565,6 +584,7 @@ def main():
             "weak": weak,
             "e2e": e2e,
             "e2e_rgba8": {"value": e2e_rgba, "unit": "frames/s", "frames_per_step": FE, "d2h_bytes_per_step": npx * 4 * FE, "something_drawn": rgba_ok,
+                          "d2h_gb_per_s": e2e_rgba * npx * 4 / 1e9, "d2h_ceiling_gb_per_s": d2h_ceiling_gbs,
                           "note": "same loop, raw RGBA8 colour planes (what DrawModel::draw's caller reads, win32.cpp:361); PCIe-bound"},
             "e2e_bgr8": {"value": e2e_bgr, "unit": "frames/s", "frames_per_step": FE, "d2h_bytes_per_step": npx * 3 * FE,
                          "note": "same loop, top-down B,G,R surfaces made by present_kernel (hana_sweep_present)"},

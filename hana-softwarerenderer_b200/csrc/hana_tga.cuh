@@ -188,15 +188,11 @@ __global__ void __launch_bounds__(TGA_THREADS, TGA_MIN_CTAS)
     }
 
     /* ---- phase 1: last T-start / last tail before each thread (block max-scan) ---- */
-    int la = -1, lt = -1;
-#pragma unroll
-    for (int j = 0; j < TGA_PPT; j++) {
-        const int i = p0 + j;
-        if (i < n) {
-            if (TGA_E(j) && !TGA_E(j - 1)) la = i;
-            if (!TGA_E(j) && TGA_E(j - 1)) lt = i;
-        }
-    }
+    /* bit j of t_starts: e(j) && !e(j-1); of tails: !e(j) && e(j-1) (a pixel beyond the image has e = 0 and no e in front) */
+    const unsigned t_starts = (EB >> 1) & ~EB & 0xFFFFu, tails = ~(EB >> 1) & EB & 0xFFFFu;
+    const int la = t_starts ? p0 + 31 - __clz((int)t_starts) : -1, lt = tails ? p0 + 31 - __clz((int)tails) : -1;
+    const unsigned stretch_ends = (EB >> 2) & ~(EB >> 1) & 0xFFFFu; /* bit j: pixel p0+j+1 is a T-start */
+    if (stretch_ends) atomicMin(&s_first, tid * TGA_PPT + (__ffs(stretch_ends) - 1));
     int ia = la, it = lt;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
@@ -222,9 +218,6 @@ __global__ void __launch_bounds__(TGA_THREADS, TGA_MIN_CTAS)
      * T-start and tail. Only the FIRST stretch end of a chunk can reach back into earlier chunks for those (every later
      * one follows a T-start inside the chunk), so all functions but that one are composed here, off the chain's critical
      * path; the first is evaluated by one thread when the carry arrives. ---- */
-    const unsigned stretch_ends = (EB >> 2) & ~(EB >> 1) & 0xFFFFu; /* bit j: pixel p0+j+1 is a T-start */
-    if (stretch_ends) atomicMin(&s_first, tid * TGA_PPT + (__ffs(stretch_ends) - 1));
-    __syncthreads();
     const int first_end = s_first; /* chunk-relative pixel index of the first stretch end; TGA_CHUNK if there is none */
     const bool owns_first = first_end >= tid * TGA_PPT && first_end < (tid + 1) * TGA_PPT;
     unsigned F = 2u; /* identity: a thread without a stretch end (the usual case) hands x through */
