@@ -347,8 +347,14 @@ def main():
     if rank == 0:
         clocks.start()
     l0 = ctx.launches
+    # per-kernel CUDA events on every step of a single-GPU run; on one step in four when the step is 1024/N frames (two events
+    # per launch cost ~0.04 ms per step: nothing against 13.7 ms, 2 % of a 128-frame step)
+    prof_every = 1 if world == 1 else 4
+    prof_on = os.environ.get("HANA_BENCH_NOPROF") != "1"
     ctx.timer_start()
-    for _ in range(args.steps):
+    for s_ in range(args.steps):
+        if prof_every > 1:
+            ctx.L.hana_ctx_profile(ctx.h, int(prof_on and s_ % prof_every == 0))
         ck(ctx.L.hana_sweep_render_dev(sweep.h, model.h, hana.BLINN, C.c_void_p(u_dev.data_ptr()), 1, F, dtex.h, ntex.h, clr,
                                        float(hana.FLT_MAX)))
     ms = ctx.timer_stop()
@@ -356,6 +362,7 @@ def main():
     clk = clocks.stop() if rank == 0 else None
     launches = ctx.launches - l0
     prof = ctx.profile_get()
+    prof_steps = len([s_ for s_ in range(args.steps) if s_ % prof_every == 0])
     ctx.profile(False, reset=False)
     overflow_batches = sweep.overflow_count() - overflow0  # batches of the timed region that dropped work: must be 0
     ms_max = max_over_ranks(ms)
@@ -599,7 +606,8 @@ def main():
             "frame_roofline": {"algorithmic_bytes_per_frame": bytes_frame, "achieved": bytes_frame * value / world / 1e9,
                                "frac": bytes_frame * value / world / 1e9 / peak, "unit": "GB/s",
                                "note": "SURVEY.md §8(d) bytes of the whole frame (both passes) over the step time per GPU"},
-            "kernel_ms_per_step": {k: v / args.steps for k, v in kernel_ms.items()},
+            "kernel_ms_per_step": {k: v / max(prof_steps, 1) for k, v in kernel_ms.items()},
+            "kernel_ms_sampled_steps": prof_steps,
             "cpu_baseline": cpu,
         }
         if extras:

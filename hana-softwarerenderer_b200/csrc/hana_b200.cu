@@ -190,6 +190,8 @@ struct hana_sweep {
         bool valid = false;
     } tga;
     uint64_t rerender_count;       /* batches rendered again by sweep_verify */
+    bool stats_lazy;               /* the last render read nothing back: statistics are still in scratch set stats_scratch */
+    int stats_scratch;
     struct Pending {
         bool active = false;
         const hana_model* model = nullptr;
@@ -398,8 +400,7 @@ static void prof_resolve(hana_ctx* ctx) {
 extern "C" int hana_ctx_profile(hana_ctx* ctx, int enable) {
     if (!ctx) return fail(HANA_E_INVALID, "ctx is NULL");
     HANA_TRY(use_device(ctx));
-    prof_resolve(ctx);
-    ctx->profile = enable != 0;
+    ctx->profile = enable != 0; /* no synchronisation: pending event pairs are resolved by profile_get / profile_reset */
     return HANA_OK;
 }
 extern "C" int hana_ctx_profile_reset(hana_ctx* ctx) {
@@ -876,10 +877,8 @@ static int run_pass(hana_ctx* ctx, const PassDesc& d) {
             c.tri_needed = tri_cap;
             c.pool_used = 1;
             c.n_work = 0xFFFFFFFFu;
-            if (d.counters_pinned)
-                HANA_TRY(post_to_host(ctx, d.counters_pinned, sc.counters, sizeof(PassCounters), st));
-            if (d.tri_counts_pinned)
-                HANA_TRY(post_to_host(ctx, d.tri_counts_pinned, sc.tri_count, sizeof(uint32_t) * d.n_frames * TRI_COUNT_WAYS, st));
+            /* statistics (triangle counts, list sizes) are not read back per batch: hana_sweep_stats fetches them from the
+             * scratch on demand */
             if (d.tri_cap_used) *d.tri_cap_used = tri_cap;
             if (d.pool_cap_used) *d.pool_cap_used = p.pool_cap;
             lists_ready = true;
@@ -1154,6 +1153,8 @@ extern "C" int hana_sweep_create(hana_ctx* ctx, int width, int height, int max_f
     s->check_tail = s->n_checks = s->next_slot = 0;
     s->overflow_batches = 0;
     s->rerender_count = 0;
+    s->stats_lazy = false;
+    s->stats_scratch = 0;
     cudaError_t e = cudaMalloc(&s->color, n * 4 * max_frames);
     if (e == cudaSuccess) e = cudaMalloc(&s->depth, n * 4 * max_frames);
     if (e == cudaSuccess) e = cudaMalloc(&s->shadow_r8, s->shadow_frame_bytes * max_frames);
@@ -1319,6 +1320,8 @@ static int sweep_render_passes(hana_sweep* s, const hana_model* model, int shade
     }
     s->last_frames = n_frames;
     s->last_clear_depth = clear_depth;
+    s->stats_lazy = lazy;
+    s->stats_scratch = d.scratch;
     memset(&s->last_stats, 0, sizeof(s->last_stats));
     s->last_stats.faces_in = (uint32_t)(model->ncorners / 3);
     s->last_stats.tile_refs = cnt[1].pool_used;
@@ -1368,14 +1371,6 @@ static int sweep_verify(hana_sweep* s) {
     CU_TRY(cudaEventSynchronize(s->ev_check[pd.slot]));
     s->pending.active = false;
     const OverflowRecord need = s->pin->need[pd.slot];
-    for (int pass = 0; pass < 2; pass++) {
-        const uint32_t* ways = s->tri_counts_pin + (size_t)pass * s->max_frames * TRI_COUNT_WAYS;
-        s->last_tri_counts[pass].assign(pd.n_frames, 0u);
-        for (int fi = 0; fi < pd.n_frames; fi++)
-            for (int w = 0; w < TRI_COUNT_WAYS; w++) s->last_tri_counts[pass][fi] += ways[(size_t)fi * TRI_COUNT_WAYS + w];
-    }
-    s->last_stats.tile_refs = s->pin->counters[1].pool_used;
-    s->last_stats.tiles_touched = s->pin->counters[1].tiles_touched;
     if (need.tri_needed <= pd.tri_cap && need.pool_needed <= pd.pool_cap) return HANA_OK;
     HANA_TRY(grow_scratch_for(ctx, need));
     s->rerender_count++;
@@ -1783,7 +1778,19 @@ extern "C" int hana_sweep_stats(hana_sweep* s, int frame, HanaStats* out) {
     CU_TRY(cudaStreamSynchronize(ctx->stream));
     *out = s->last_stats;
     out->pixels_covered = px;
-    if (frame < (int)s->last_tri_counts[1].size()) out->tris_out = s->last_tri_counts[1][frame];
+    if (s->stats_lazy) { /* the main pass's counters are still where it left them */
+        const Scratch& sc = s->stats_scratch ? ctx->sc2 : ctx->sc;
+        PassCounters c;
+        uint32_t ways[TRI_COUNT_WAYS];
+        CU_TRY(cudaMemcpy(&c, sc.counters, sizeof(c), cudaMemcpyDeviceToHost));
+        CU_TRY(cudaMemcpy(ways, sc.tri_count + (size_t)frame * TRI_COUNT_WAYS, sizeof(ways), cudaMemcpyDeviceToHost));
+        out->tile_refs = c.pool_used;
+        out->tiles_touched = c.tiles_touched;
+        out->tris_out = 0;
+        for (int w = 0; w < TRI_COUNT_WAYS; w++) out->tris_out += ways[w];
+    } else if (frame < (int)s->last_tri_counts[1].size()) {
+        out->tris_out = s->last_tri_counts[1][frame];
+    }
     return HANA_OK;
 }
 

@@ -924,7 +924,10 @@ __global__ void __launch_bounds__(RW_THREADS, ShaderAttrs<SHADER>::LIT ? HANA_OC
                 }
             }
             __syncwarp();
-            for (int j = 0; j < n; j++) {
+            /* last record first: the resolve is order-free (smallest depth, then largest key), and a list is filled roughly in
+             * submission order, so scenes drawn back to front (BASELINE.json configs[4]) meet their nearest layer first and
+             * the layers behind it fail the depth test instead of each winning, parking weights and being overwritten */
+            for (int j = n - 1; j >= 0; j--) {
                 const float4 r0 = wt.tri[j * RW_REC_Q + 0]; /* ax, ay, s0x, s0y */
                 const float4 r1 = wt.tri[j * RW_REC_Q + 1]; /* s1x, s1y, uz, thr */
                 const float4 r4 = wt.tri[j * RW_REC_Q + 4]; /* slot, key, exchanged, mask */
