@@ -176,13 +176,15 @@ struct hana_sweep {
     size_t present_cap;
     /* RLE TGA files made on the device (hana_sweep_encode_tga / hana_sweep_fetch_tga) */
     struct Tga {
-        uint8_t* slots = nullptr;      /* [count] worst-case slots the encoder writes */
-        uint8_t* packed = nullptr;     /* the files back to back (16-byte aligned starts) */
-        size_t cap_frames = 0, slot_bytes = 0;
-        TgaCarry* carry = nullptr;     /* [max_frames] */
+        uint8_t* packed = nullptr;     /* the files back to back (16-byte aligned starts), written in place by tga_write_kernel */
+        size_t cap_frames = 0, worst_bytes = 0;
+        uint32_t* ebits = nullptr;     /* [count][estride] equal-neighbour bits, 32 pixels per word */
+        TgaRec* recs = nullptr;        /* [count][rstride] state at the first pixel of every word */
+        uint8_t* counts = nullptr;     /* [count][rstride] bytes each word emits */
+        uint32_t* batch_sums = nullptr;            /* [count][nbatch] */
+        unsigned long long* batch_offs = nullptr;  /* [count][nbatch] */
         unsigned long long* sizes = nullptr;   /* device [max_frames] */
         unsigned long long* offsets = nullptr; /* device [max_frames + 1] */
-        unsigned int* ticket = nullptr;
         unsigned long long* meta_pin = nullptr; /* pinned: offsets [max_frames + 1], then sizes [max_frames] */
         cudaEvent_t ev = nullptr;
         int first = 0, count = 0;      /* what the last encode covered */
@@ -1201,8 +1203,8 @@ extern "C" int hana_sweep_destroy(hana_sweep* s) {
     if (s->tri_counts_pin) cudaFreeHost(s->tri_counts_pin);
     if (s->ev_render) cudaEventDestroy(s->ev_render);
     if (s->ev_copy) cudaEventDestroy(s->ev_copy);
-    cudaFree(s->tga.slots); cudaFree(s->tga.packed); cudaFree(s->tga.carry); cudaFree(s->tga.sizes); cudaFree(s->tga.offsets);
-    cudaFree(s->tga.ticket);
+    cudaFree(s->tga.packed); cudaFree(s->tga.ebits); cudaFree(s->tga.recs); cudaFree(s->tga.counts); cudaFree(s->tga.batch_sums);
+    cudaFree(s->tga.batch_offs); cudaFree(s->tga.sizes); cudaFree(s->tga.offsets);
     if (s->tga.meta_pin) cudaFreeHost(s->tga.meta_pin);
     if (s->tga.ev) cudaEventDestroy(s->tga.ev);
     for (auto ev : s->ev_check)
@@ -1646,44 +1648,49 @@ static int tga_encode_launch(hana_sweep* s, int first, int count) {
     hana_ctx* ctx = s->ctx;
     hana_sweep::Tga& t = s->tga;
     const size_t npix = (size_t)s->w * s->h;
-    const size_t slot_bytes = tga_slot_bytes(npix);
+    const size_t worst = tga_worst_bytes(npix);
+    const TgaLayout L = tga_layout(s->w, s->h);
     if (s->copy_in_flight) { /* the previous fetch reads the packed buffer */
         CU_TRY(cudaStreamWaitEvent(ctx->stream, s->ev_copy, 0));
         s->copy_in_flight = false;
     }
-    const unsigned chunks = (unsigned)((npix + TGA_CHUNK - 1) / TGA_CHUNK);
     if (!t.sizes) {
         CU_TRY(cudaMalloc(&t.sizes, sizeof(unsigned long long) * s->max_frames));
         CU_TRY(cudaMalloc(&t.offsets, sizeof(unsigned long long) * (s->max_frames + 1)));
-        CU_TRY(cudaMalloc(&t.ticket, sizeof(unsigned int)));
         CU_TRY(cudaMallocHost(&t.meta_pin, sizeof(unsigned long long) * (2 * (size_t)s->max_frames + 1)));
         CU_TRY(cudaEventCreateWithFlags(&t.ev, cudaEventDisableTiming));
     }
-    if ((size_t)count > t.cap_frames || slot_bytes != t.slot_bytes) {
+    if ((size_t)count > t.cap_frames || worst != t.worst_bytes) {
         CU_TRY(cudaStreamSynchronize(ctx->stream));
         CU_TRY(cudaStreamSynchronize(ctx->copy_stream));
-        cudaFree(t.slots);
-        cudaFree(t.packed);
-        cudaFree(t.carry);
-        t.slots = t.packed = nullptr;
-        t.carry = nullptr;
+        cudaFree(t.packed); cudaFree(t.ebits); cudaFree(t.recs); cudaFree(t.counts); cudaFree(t.batch_sums); cudaFree(t.batch_offs);
+        t.packed = nullptr; t.ebits = nullptr; t.recs = nullptr; t.counts = nullptr; t.batch_sums = nullptr; t.batch_offs = nullptr;
         t.cap_frames = 0;
-        CU_TRY(cudaMalloc(&t.carry, sizeof(TgaCarry) * (size_t)count * (chunks + 1))); /* one mailbox per (frame, chunk) */
-        CU_TRY(cudaMalloc(&t.slots, slot_bytes * count));
-        CU_TRY(cudaMalloc(&t.packed, slot_bytes * count));
+        CU_TRY(cudaMalloc(&t.packed, worst * count));
+        CU_TRY(cudaMalloc(&t.ebits, sizeof(uint32_t) * L.estride * count));
+        CU_TRY(cudaMalloc(&t.recs, sizeof(TgaRec) * L.rstride * count));
+        CU_TRY(cudaMalloc(&t.counts, L.rstride * count));
+        CU_TRY(cudaMalloc(&t.batch_sums, sizeof(uint32_t) * (size_t)L.nbatch * count));
+        CU_TRY(cudaMalloc(&t.batch_offs, sizeof(unsigned long long) * (size_t)L.nbatch * count));
         t.cap_frames = (size_t)count;
-        t.slot_bytes = slot_bytes;
+        t.worst_bytes = worst;
     }
-    CU_TRY(cudaMemsetAsync(t.ticket, 0, sizeof(unsigned int), ctx->stream));
-    CU_TRY(cudaMemsetAsync(t.carry, 0, sizeof(TgaCarry) * (size_t)count * (chunks + 1), ctx->stream));
     cudaEvent_t a, b;
     prof_begin(ctx, PROF_OTHER, &a, &b);
-    tga_rle_kernel<<<chunks * (unsigned)count, TGA_THREADS, 0, ctx->stream>>>(s->color, npix, first, s->w, s->h, count, t.slots, slot_bytes,
-                                                                          t.carry, t.sizes, t.ticket);
+    const dim3 egrid((unsigned)((L.estride + 32 * (TGA_E_THREADS / 32) - 1) / (32 * (TGA_E_THREADS / 32))), (unsigned)count);
+    if (s->w % 4 == 0 && s->w >= 128)
+        tga_ebits_kernel<true><<<egrid, TGA_E_THREADS, 0, ctx->stream>>>(s->color, npix, first, s->w, s->h, t.ebits, L);
+    else
+        tga_ebits_kernel<false><<<egrid, TGA_E_THREADS, 0, ctx->stream>>>(s->color, npix, first, s->w, s->h, t.ebits, L);
+    tga_structure_kernel<<<(unsigned)count, TGA_B_THREADS, 0, ctx->stream>>>(t.ebits, t.recs, L);
+    const dim3 cgrid((unsigned)((L.nbatch + TGA_C_THREADS / 32 - 1) / (TGA_C_THREADS / 32)), (unsigned)count);
+    tga_count_kernel<<<cgrid, TGA_C_THREADS, 0, ctx->stream>>>(t.ebits, t.recs, t.counts, t.batch_sums, L);
+    tga_scan_kernel<<<(unsigned)count, TGA_S_THREADS, 0, ctx->stream>>>(t.batch_sums, t.batch_offs, t.sizes, L.nbatch);
     tga_offsets_kernel<<<1, 32, 0, ctx->stream>>>(t.sizes, t.offsets, count);
-    tga_pack_kernel<<<dim3(64, (unsigned)count), 256, 0, ctx->stream>>>(t.slots, slot_bytes, t.sizes, t.offsets, t.packed);
+    tga_write_kernel<<<cgrid, TGA_C_THREADS, 0, ctx->stream>>>(s->color, npix, first, s->w, s->h, t.ebits, t.recs, t.counts, t.batch_offs, t.sizes,
+                                                               t.offsets, t.packed, L);
     prof_end(ctx, PROF_OTHER, a, b);
-    ctx->launches += 3;
+    ctx->launches += 6;
     CU_TRY(cudaGetLastError());
     HANA_TRY(post_to_host(ctx, t.meta_pin, t.offsets, sizeof(unsigned long long) * (count + 1), ctx->stream));
     HANA_TRY(post_to_host(ctx, t.meta_pin + s->max_frames + 1, t.sizes, sizeof(unsigned long long) * count, ctx->stream));

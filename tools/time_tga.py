@@ -15,7 +15,11 @@ from hana_softwarerenderer_b200.api import PinnedBuffer  # noqa: E402
 ctx = hana.Context(0)
 sc = hana.load_bundled("african_head", None, 3)
 model, dtex, ntex = sc.upload(ctx)
-for (W, H, F) in ((1920, 1080, 1), (1920, 1080, 16), (960, 540, 16), (3840, 2160, 4), (1920, 1080, 128), (1920, 1080, 512)):
+CASES = ((1920, 1080, 1), (1920, 1080, 16), (960, 540, 16), (3840, 2160, 4), (1920, 1080, 128), (1920, 1080, 512))
+if os.environ.get('TGA_CASES'):
+    CASES = tuple(tuple(int(v) for v in c.split('x')) for c in os.environ['TGA_CASES'].split(','))
+REPS = int(os.environ.get('TGA_REPS', '4'))
+for (W, H, F) in CASES:
     sw = ctx.sweep(W, H, F)
     arr = hana.orbit_sweep_uniforms(W, H, 0, F, frames_per_turn=1024)
     sw.render(model, hana.BLINN, arr, dtex, ntex)
@@ -24,7 +28,7 @@ for (W, H, F) in ((1920, 1080, 1), (1920, 1080, 16), (960, 540, 16), (3840, 2160
     offs = (C.c_uint64 * (F + 1))()
     szs = (C.c_uint64 * F)()
     best = 1e9
-    for rep in range(4):
+    for rep in range(REPS):
         ctx.timer_start()
         assert ctx.L.hana_sweep_encode_tga(sw.h, 0, F) == 0
         ms_enc = ctx.timer_stop()
