@@ -87,9 +87,24 @@ struct hana_ctx {
     EncodeTiledFn encode = nullptr;
     Scratch sc;
     Scratch sc2;                          /* second set: the main pass is binned on side_stream beside the shadow pass */
+    Scratch sc3, sc4;                     /* the same two for every other submission of a pipelined sweep (below) */
     cudaStream_t side_stream = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    /* Pipelined sweeps: the two passes of submission k+1 are binned (bin_stream, side_stream; scratch sets of the other
+     * parity) while the rasterisers of submission k still run on `stream`, so the fixed cost of a submission — eight
+     * small dependent kernels in front of the first rasteriser, the rasterisers' tails — is hidden behind its neighbours.
+     * A rasteriser waits for its pass's binning (ev_bin), a binning for the rasterisers that last read its scratch set
+     * and uniform block (ev_raster_done of the same parity), and for whatever serial work used sets 0/1 since (ev_serial). */
+    cudaStream_t bin_stream = nullptr;
+    cudaEvent_t ev_bin[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}}; /* [parity][pass] */
+    cudaEvent_t ev_raster_done[2] = {nullptr, nullptr};
+    bool raster_done_valid[2] = {false, false};
+    cudaEvent_t ev_serial = nullptr;
+    bool serial_dirty = false;
+    int parity = 0;
+    bool pipeline = true;                 /* HANA_NO_PIPELINE=1 in the environment: one submission after the other */
     uint32_t tri_cap_hint = 0;
+    size_t pool_hint = 0;                 /* list records a batch has needed so far: what a scratch set is created with */
     HanaUniforms* u_raw = nullptr;  /* device, 1 */
     DevUniforms* u_dev = nullptr;   /* device, 1 */
     uint32_t* stat_pixels = nullptr; /* device, 1 */
@@ -112,6 +127,8 @@ struct hana_ctx {
     uint32_t r8_slot_limit = R8_SLOT_LIMIT; /* HANA_R8_SLOT_LIMIT in the environment lowers it (tests force the WIDE variant) */
     uint64_t wide_r8_launches = 0;
 };
+
+static Scratch& scratch_of(hana_ctx* ctx, int i) { return i == 0 ? ctx->sc : i == 1 ? ctx->sc2 : i == 2 ? ctx->sc3 : ctx->sc4; }
 
 struct hana_model {
     hana_ctx* ctx;
@@ -143,7 +160,8 @@ struct hana_sweep {
     bool tma_ok;
     CUtensorMap tm_color, tm_depth, tm_r8;
     HanaUniforms* u_raw;
-    DevUniforms* u_dev;
+    DevUniforms* u_dev;            /* the block the last submission used: u_dev_buf + parity * max_frames */
+    DevUniforms* u_dev_buf;        /* device [2][max_frames]: consecutive pipelined submissions alternate */
     unsigned long long* checksums;
     uint32_t* pix_counts;
     int last_frames;
@@ -152,7 +170,8 @@ struct hana_sweep {
     std::vector<uint32_t> last_tri_counts[2];
     /* asynchronous rendering: a render is launched without any read-back; what it needed is checked (and the batch
      * re-rendered with larger scratch if something was dropped) at the sweep's next synchronisation point */
-    OverflowRecord* overflow;      /* device */
+    OverflowRecord* overflow;      /* device: the record the last submission used (overflow_buf + parity) */
+    OverflowRecord* overflow_buf;  /* device [2] */
     /* A render that is superseded by the next one before anybody synchronised with it (back-to-back submissions) is
      * not forgotten: its needs land in a slot of their own and are examined, without blocking, at later calls; a batch
      * that ran out of scratch is counted (hana_sweep_overflow_count) and the scratch grows for the batches that follow. */
@@ -266,7 +285,14 @@ extern "C" int hana_ctx_create(int device, hana_ctx** out) {
                                          "; this library contains sm_100a code only");
     }
     ctx->sm_count = prop.multiProcessorCount;
-    CU_TRY(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
+    {
+        /* the stream the rasterisers run on outranks the streams that bin the next submission beside them: CTAs of a
+         * waiting rasteriser take free SM slots first, binning fills what the rasterisers' tails leave idle */
+        int prio_lo = 0, prio_hi = 0;
+        CU_TRY(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+        const char* np = getenv("HANA_NO_STREAM_PRIO");
+        CU_TRY(cudaStreamCreateWithPriority(&ctx->own_stream, cudaStreamNonBlocking, (np && np[0] == '1') ? prio_lo : prio_hi));
+    }
     CU_TRY(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
     ctx->stream = ctx->own_stream;
     void* fn = nullptr;
@@ -287,9 +313,19 @@ extern "C" int hana_ctx_create(int device, hana_ctx** out) {
     CU_TRY(cudaMalloc(&ctx->stat_pixels, sizeof(uint32_t)));
     CU_TRY(cudaMalloc(&ctx->sc.counters, sizeof(PassCounters)));
     CU_TRY(cudaMallocHost(&ctx->sc.counters_host, sizeof(PassCounters)));
-    CU_TRY(cudaMalloc(&ctx->sc2.counters, sizeof(PassCounters)));
-    CU_TRY(cudaMallocHost(&ctx->sc2.counters_host, sizeof(PassCounters)));
+    for (int i = 1; i < 4; i++) {
+        CU_TRY(cudaMalloc(&scratch_of(ctx, i).counters, sizeof(PassCounters)));
+        CU_TRY(cudaMallocHost(&scratch_of(ctx, i).counters_host, sizeof(PassCounters)));
+    }
     CU_TRY(cudaStreamCreateWithFlags(&ctx->side_stream, cudaStreamNonBlocking));
+    CU_TRY(cudaStreamCreateWithFlags(&ctx->bin_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; i++) {
+        CU_TRY(cudaEventCreateWithFlags(&ctx->ev_bin[i][0], cudaEventDisableTiming));
+        CU_TRY(cudaEventCreateWithFlags(&ctx->ev_bin[i][1], cudaEventDisableTiming));
+        CU_TRY(cudaEventCreateWithFlags(&ctx->ev_raster_done[i], cudaEventDisableTiming));
+    }
+    CU_TRY(cudaEventCreateWithFlags(&ctx->ev_serial, cudaEventDisableTiming));
+    if (const char* np = getenv("HANA_NO_PIPELINE")) ctx->pipeline = !(np[0] == '1');
     CU_TRY(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
     CU_TRY(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
     CU_TRY(cudaEventCreate(&ctx->t0));
@@ -308,13 +344,15 @@ extern "C" int hana_ctx_destroy(hana_ctx* ctx) {
     if (ctx->host_sweep) hana_sweep_destroy(ctx->host_sweep);
     if (ctx->host_frame) hana_rb_destroy(ctx->host_frame);
     if (ctx->host_shadow) hana_rb_destroy(ctx->host_shadow);
-    for (Scratch* sp : {&ctx->sc, &ctx->sc2}) {
+    for (Scratch* sp : {&ctx->sc, &ctx->sc2, &ctx->sc3, &ctx->sc4}) {
         Scratch& s = *sp;
         cudaFree(s.tri_rec); cudaFree(s.tri_attr); cudaFree(s.tri_bbox); cudaFree(s.tri_count); cudaFree(s.tile_arrays);
         cudaFree(s.tile_recs); cudaFree(s.work); cudaFree(s.counters); cudaFreeHost(s.counters_host); cudaFree(s.vis);
     }
     cudaStreamDestroy(ctx->side_stream);
-    cudaEventDestroy(ctx->ev_fork); cudaEventDestroy(ctx->ev_join);
+    cudaStreamDestroy(ctx->bin_stream);
+    cudaEventDestroy(ctx->ev_fork); cudaEventDestroy(ctx->ev_join); cudaEventDestroy(ctx->ev_serial);
+    for (int i = 0; i < 2; i++) { cudaEventDestroy(ctx->ev_bin[i][0]); cudaEventDestroy(ctx->ev_bin[i][1]); cudaEventDestroy(ctx->ev_raster_done[i]); }
     cudaFree(ctx->u_raw); cudaFree(ctx->u_dev); cudaFree(ctx->stat_pixels);
     for (auto& p : ctx->prof_pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
     for (auto e : ctx->ev_pool) cudaEventDestroy(e);
@@ -342,6 +380,8 @@ extern "C" int hana_sync(hana_ctx* ctx) {
         HANA_TRY(sweep_verify(s)); /* re-renders a batch that ran out of scratch */
     }
     CU_TRY(cudaStreamSynchronize(ctx->stream));
+    CU_TRY(cudaStreamSynchronize(ctx->bin_stream));
+    CU_TRY(cudaStreamSynchronize(ctx->side_stream));
     CU_TRY(cudaStreamSynchronize(ctx->copy_stream));
     return HANA_OK;
 }
@@ -687,7 +727,8 @@ struct PassDesc {
     uint32_t* pool_cap_used = nullptr;
     /* split passes (lazy only): phase 1 = setup + scan + fill on `stream` with scratch set `scratch`, phase 2 = raster */
     int phase = 0;
-    int scratch = 0;
+    int scratch = 0;      /* scratch set 0..3 */
+    bool pipelined = false; /* part of a pipelined sweep submission: does not count as serial use of sets 0/1 */
     int band_first = 0, band_count = 0; /* tile rows of a split frame; count 0 = the whole frame */
     cudaStream_t stream = nullptr;
 };
@@ -699,6 +740,7 @@ static int grow(T** ptr, size_t* cap, size_t need, hana_ctx* ctx) {
     n = std::max<size_t>(n, 1);
     CU_TRY(cudaStreamSynchronize(ctx->stream));
     CU_TRY(cudaStreamSynchronize(ctx->side_stream));
+    CU_TRY(cudaStreamSynchronize(ctx->bin_stream));
     if (*ptr) CU_TRY(cudaFree(*ptr));
     *ptr = nullptr;
     *cap = 0;
@@ -761,8 +803,9 @@ static int run_pass(hana_ctx* ctx, const PassDesc& d) {
     if (tiles_x > 1024 || tiles_y > 1024) return fail(HANA_E_INVALID, "target larger than 16384 pixels on a side");
     if (d.n_frames < 1 || d.n_frames > 4096) return fail(HANA_E_INVALID, "1..4096 frames per batch");
     const int nfaces = d.model->ncorners / 3;
-    Scratch& sc = d.scratch ? ctx->sc2 : ctx->sc;
+    Scratch& sc = scratch_of(ctx, d.scratch);
     cudaStream_t st = d.stream ? d.stream : ctx->stream;
+    if (!d.pipelined) ctx->serial_dirty = true;
     const size_t tiles_total = n_tiles * d.n_frames;
     if (tiles_total > 0xFFFFFFF0ull) return fail(HANA_E_INVALID, "frames x tiles exceeds 32 bits");
 
@@ -798,7 +841,8 @@ static int run_pass(hana_ctx* ctx, const PassDesc& d) {
         const bool use_vis = d.mode != MODE_RMW && !d.setup_only && (size_t)nfaces * 16 >= (size_t)d.W * d.H && !getenv("HANA_NO_VIS");
         if (use_vis) HANA_TRY(grow(&sc.vis, &sc.vis_cap, (size_t)d.W * d.H * d.n_frames, ctx));
         HANA_TRY(grow(&sc.work, &sc.work_cap, tiles_total, ctx));
-        if (!sc.tile_recs) HANA_TRY(grow(&sc.tile_recs, &sc.pool_cap, std::max<size_t>(tri_total * 2, 65536) * 4, ctx));
+        if (!sc.tile_recs || sc.pool_cap / 4 < ctx->pool_hint)
+            HANA_TRY(grow(&sc.tile_recs, &sc.pool_cap, std::max<size_t>(std::max<size_t>(tri_total * 2, 65536), ctx->pool_hint) * 4, ctx));
 
         p.posu = d.model->posu;
         p.nrmv = d.model->nrmv;
@@ -993,12 +1037,13 @@ static int run_pass(hana_ctx* ctx, const PassDesc& d) {
     return HANA_OK;
 }
 
-static int upload_uniforms(hana_ctx* ctx, const HanaUniforms* host, int n, HanaUniforms* raw_dev, DevUniforms* dev) {
-    if (host) CU_TRY(cudaMemcpyAsync(raw_dev, host, sizeof(HanaUniforms) * n, cudaMemcpyHostToDevice, ctx->stream));
+static int upload_uniforms(hana_ctx* ctx, const HanaUniforms* host, int n, HanaUniforms* raw_dev, DevUniforms* dev, cudaStream_t st = nullptr) {
+    if (!st) st = ctx->stream;
+    if (host) CU_TRY(cudaMemcpyAsync(raw_dev, host, sizeof(HanaUniforms) * n, cudaMemcpyHostToDevice, st));
     cudaEvent_t a, b;
-    prof_begin(ctx, PROF_BEGIN, &a, &b);
-    begin_kernel<<<(n + 63) / 64, 64, 0, ctx->stream>>>(raw_dev, dev, n);
-    prof_end(ctx, PROF_BEGIN, a, b);
+    prof_begin(ctx, PROF_BEGIN, &a, &b, st);
+    begin_kernel<<<(n + 63) / 64, 64, 0, st>>>(raw_dev, dev, n);
+    prof_end(ctx, PROF_BEGIN, a, b, st);
     ctx->launches++;
     CU_TRY(cudaGetLastError());
     return HANA_OK;
@@ -1148,7 +1193,7 @@ extern "C" int hana_sweep_create(hana_ctx* ctx, int width, int height, int max_f
     size_t n = (size_t)width * height;
     s->shadow_pitch = (width + 15) / 16 * 16;
     s->shadow_frame_bytes = (size_t)s->shadow_pitch * ((height + 15) / 16 * 16);
-    s->color = nullptr; s->depth = nullptr; s->shadow_r8 = nullptr; s->u_raw = nullptr; s->u_dev = nullptr;
+    s->color = nullptr; s->depth = nullptr; s->shadow_r8 = nullptr; s->u_raw = nullptr; s->u_dev = nullptr; s->u_dev_buf = nullptr; s->overflow_buf = nullptr;
     s->checksums = nullptr; s->pix_counts = nullptr; s->overflow = nullptr; s->pin = nullptr; s->tri_counts_pin = nullptr;
     s->ev_render = nullptr; s->ev_copy = nullptr; s->copy_in_flight = false; s->present_buf = nullptr; s->present_cap = 0;
     for (auto& e : s->ev_check) e = nullptr;
@@ -1161,10 +1206,12 @@ extern "C" int hana_sweep_create(hana_ctx* ctx, int width, int height, int max_f
     if (e == cudaSuccess) e = cudaMalloc(&s->depth, n * 4 * max_frames);
     if (e == cudaSuccess) e = cudaMalloc(&s->shadow_r8, s->shadow_frame_bytes * max_frames);
     if (e == cudaSuccess) e = cudaMalloc(&s->u_raw, sizeof(HanaUniforms) * max_frames);
-    if (e == cudaSuccess) e = cudaMalloc(&s->u_dev, sizeof(DevUniforms) * max_frames);
+    if (e == cudaSuccess) e = cudaMalloc(&s->u_dev_buf, sizeof(DevUniforms) * max_frames * 2);
+    s->u_dev = s->u_dev_buf;
     if (e == cudaSuccess) e = cudaMalloc(&s->checksums, sizeof(unsigned long long) * max_frames);
     if (e == cudaSuccess) e = cudaMalloc(&s->pix_counts, sizeof(uint32_t) * max_frames);
-    if (e == cudaSuccess) e = cudaMalloc(&s->overflow, sizeof(OverflowRecord));
+    if (e == cudaSuccess) e = cudaMalloc(&s->overflow_buf, sizeof(OverflowRecord) * 2);
+    s->overflow = s->overflow_buf;
     if (e == cudaSuccess) e = cudaMallocHost(&s->pin, sizeof(*s->pin));
     if (e == cudaSuccess) e = cudaMallocHost(&s->tri_counts_pin, sizeof(uint32_t) * 2 * max_frames * TRI_COUNT_WAYS);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev_render, cudaEventDisableTiming);
@@ -1197,8 +1244,8 @@ extern "C" int hana_sweep_destroy(hana_sweep* s) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     cudaStreamSynchronize(ctx->copy_stream);
-    cudaFree(s->color); cudaFree(s->depth); cudaFree(s->shadow_r8); cudaFree(s->u_raw); cudaFree(s->u_dev);
-    cudaFree(s->checksums); cudaFree(s->pix_counts); cudaFree(s->overflow); cudaFree(s->present_buf);
+    cudaFree(s->color); cudaFree(s->depth); cudaFree(s->shadow_r8); cudaFree(s->u_raw); cudaFree(s->u_dev_buf);
+    cudaFree(s->checksums); cudaFree(s->pix_counts); cudaFree(s->overflow_buf); cudaFree(s->present_buf);
     if (s->pin) cudaFreeHost(s->pin);
     if (s->tri_counts_pin) cudaFreeHost(s->tri_counts_pin);
     if (s->ev_render) cudaEventDestroy(s->ev_render);
@@ -1219,8 +1266,9 @@ extern "C" int hana_sweep_destroy(hana_sweep* s) {
 enum { SWEEP_PASS_SHADOW = 1, SWEEP_PASS_MAIN = 2, SWEEP_PASS_BOTH = 3 };
 static int sweep_render_passes(hana_sweep* s, const hana_model* model, int shader_id, int enable_shadow, int n_frames,
                                const hana_texture* diffuse, const hana_texture* normal, const uint8_t clear_rgba[4],
-                               float clear_depth, bool lazy, int passes = SWEEP_PASS_BOTH) {
+                               float clear_depth, bool lazy, int passes = SWEEP_PASS_BOTH, int pipe_parity = -1) {
     hana_ctx* ctx = s->ctx;
+    const bool pipe = pipe_parity >= 0; /* lazy, both passes: binned on bin_stream / side_stream with this parity's scratch sets */
     PassCounters cnt[2];
     memset(cnt, 0, sizeof(cnt));
     PassDesc shadow_desc;
@@ -1251,11 +1299,18 @@ static int sweep_render_passes(hana_sweep* s, const hana_model* model, int shade
         d.band_first = s->band[0][0];
         d.band_count = s->band[0][1];
         if (lazy && passes == SWEEP_PASS_BOTH) { /* fork: the main pass is binned on the side stream while this one is binned here */
-            CU_TRY(cudaEventRecord(ctx->ev_fork, ctx->stream));
+            cudaStream_t bst = pipe ? ctx->bin_stream : ctx->stream;
+            CU_TRY(cudaEventRecord(ctx->ev_fork, bst));
             CU_TRY(cudaStreamWaitEvent(ctx->side_stream, ctx->ev_fork, 0));
             d.phase = 1;
+            if (pipe) {
+                d.scratch = 2 * pipe_parity;
+                d.stream = ctx->bin_stream;
+                d.pipelined = true;
+            }
         }
         HANA_TRY(run_pass(ctx, d));
+        if (pipe) CU_TRY(cudaEventRecord(ctx->ev_bin[pipe_parity][0], ctx->bin_stream));
         shadow_desc = d;
     }
     if (!(passes & SWEEP_PASS_MAIN)) {
@@ -1303,13 +1358,17 @@ static int sweep_render_passes(hana_sweep* s, const hana_model* model, int shade
     d.pool_cap_used = &pc;
     if (lazy && enable_shadow && passes == SWEEP_PASS_BOTH) {
         d.phase = 1;
-        d.scratch = 1;
+        d.scratch = pipe ? 2 * pipe_parity + 1 : 1;
         d.stream = ctx->side_stream;
+        d.pipelined = pipe;
         HANA_TRY(run_pass(ctx, d));
-        CU_TRY(cudaEventRecord(ctx->ev_join, ctx->side_stream));
+        cudaEvent_t joined = pipe ? ctx->ev_bin[pipe_parity][1] : ctx->ev_join;
+        CU_TRY(cudaEventRecord(joined, ctx->side_stream));
+        if (pipe) CU_TRY(cudaStreamWaitEvent(ctx->stream, ctx->ev_bin[pipe_parity][0], 0));
         shadow_desc.phase = 2;
+        shadow_desc.stream = nullptr;
         HANA_TRY(run_pass(ctx, shadow_desc)); /* shadow rasteriser */
-        CU_TRY(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
+        CU_TRY(cudaStreamWaitEvent(ctx->stream, joined, 0));
         d.phase = 2;
         d.stream = nullptr;
         HANA_TRY(run_pass(ctx, d));           /* main rasteriser */
@@ -1333,9 +1392,10 @@ static int sweep_render_passes(hana_sweep* s, const hana_model* model, int shade
 
 static int grow_scratch_for(hana_ctx* ctx, const OverflowRecord& need) {
     ctx->tri_cap_hint = std::max(ctx->tri_cap_hint, need.tri_needed + need.tri_needed / 8 + 64);
-    for (Scratch* sp : {&ctx->sc, &ctx->sc2}) /* headroom for the other frames of an orbit */
-        if ((size_t)need.pool_needed > sp->pool_cap / 4 && (sp == &ctx->sc || sp->tile_recs))
-            HANA_TRY(grow(&sp->tile_recs, &sp->pool_cap, ((size_t)need.pool_needed + need.pool_needed / 4) * 4, ctx));
+    ctx->pool_hint = std::max(ctx->pool_hint, (size_t)need.pool_needed + need.pool_needed / 4); /* headroom for the other frames of an orbit */
+    for (Scratch* sp : {&ctx->sc, &ctx->sc2, &ctx->sc3, &ctx->sc4})
+        if (ctx->pool_hint > sp->pool_cap / 4 && (sp == &ctx->sc || sp->tile_recs))
+            HANA_TRY(grow(&sp->tile_recs, &sp->pool_cap, ctx->pool_hint * 4, ctx));
     return HANA_OK;
 }
 
@@ -1382,7 +1442,7 @@ static int sweep_verify(hana_sweep* s) {
 
 static int sweep_render_common(hana_sweep* s, const hana_model* model, int shader_id, const HanaUniforms* host_uniforms,
                                int enable_shadow, int n_frames, const hana_texture* diffuse, const hana_texture* normal,
-                               const uint8_t clear_rgba[4], float clear_depth) {
+                               const uint8_t clear_rgba[4], float clear_depth, const void* uniforms_dev = nullptr) {
     hana_ctx* ctx = s->ctx;
     /* the previous render's frames are about to be overwritten: it cannot be rendered again, but what it needed is
      * still examined once it has completed (sweep_poll_checks); its copies must be out */
@@ -1404,14 +1464,41 @@ static int sweep_render_common(hana_sweep* s, const hana_model* model, int shade
         CU_TRY(cudaStreamWaitEvent(ctx->stream, s->ev_copy, 0));
         s->copy_in_flight = false;
     }
-    HANA_TRY(upload_uniforms(ctx, host_uniforms, n_frames, s->u_raw, s->u_dev));
-    CU_TRY(cudaMemsetAsync(s->overflow, 0, sizeof(OverflowRecord), ctx->stream));
-    HANA_TRY(sweep_render_passes(s, model, shader_id, enable_shadow, n_frames, diffuse, normal, clear_rgba, clear_depth, true));
+    /* two-pass submissions on the context's own stream are pipelined (hana_ctx: bin_stream); a caller's stream
+     * (hana_ctx_set_stream) keeps everything in that stream's order */
+    const bool pipe = enable_shadow && ctx->pipeline && ctx->stream == ctx->own_stream;
+    int parity = -1;
+    cudaStream_t ust = ctx->stream; /* where the uniforms are made ready */
+    if (pipe) {
+        parity = ctx->parity;
+        ctx->parity ^= 1;
+        ust = ctx->bin_stream;
+        if (ctx->raster_done_valid[parity]) CU_TRY(cudaStreamWaitEvent(ust, ctx->ev_raster_done[parity], 0));
+        if (ctx->serial_dirty) { /* draws / single-pass sweeps since the last pipelined submission used sets 0 / 1 on `stream` */
+            CU_TRY(cudaEventRecord(ctx->ev_serial, ctx->stream));
+            CU_TRY(cudaStreamWaitEvent(ust, ctx->ev_serial, 0));
+            ctx->serial_dirty = false;
+        }
+    }
+    s->u_dev = s->u_dev_buf + (size_t)(pipe ? parity : 0) * s->max_frames;
+    s->overflow = s->overflow_buf + (pipe ? parity : 0);
+    if (uniforms_dev && uniforms_dev != s->u_raw)
+        CU_TRY(cudaMemcpyAsync(s->u_raw, uniforms_dev, sizeof(HanaUniforms) * n_frames, cudaMemcpyDeviceToDevice, ust));
+    HANA_TRY(upload_uniforms(ctx, host_uniforms, n_frames, s->u_raw, s->u_dev, ust));
+    CU_TRY(cudaMemsetAsync(s->overflow, 0, sizeof(OverflowRecord), ust));
+    const bool dirty_before = ctx->serial_dirty;
+    HANA_TRY(sweep_render_passes(s, model, shader_id, enable_shadow, n_frames, diffuse, normal, clear_rgba, clear_depth, true,
+                                 SWEEP_PASS_BOTH, parity));
+    if (pipe) ctx->serial_dirty = dirty_before;
     const int slot = s->next_slot;
     s->next_slot = (slot + 1) % (hana_sweep::CHECK_RING + 1);
     HANA_TRY(post_to_host(ctx, &s->pin->need[slot], s->overflow, sizeof(OverflowRecord), ctx->stream));
     CU_TRY(cudaEventRecord(s->ev_check[slot], ctx->stream));
     CU_TRY(cudaEventRecord(s->ev_render, ctx->stream));
+    if (pipe) {
+        CU_TRY(cudaEventRecord(ctx->ev_raster_done[parity], ctx->stream));
+        ctx->raster_done_valid[parity] = true;
+    }
     hana_sweep::Pending& pd = s->pending;
     pd.active = true;
     pd.slot = slot;
@@ -1450,10 +1537,8 @@ extern "C" int hana_sweep_render_dev(hana_sweep* s, const hana_model* model, int
     if (n_frames < 1 || n_frames > s->max_frames) return fail(HANA_E_INVALID, "n_frames outside 1..max_frames");
     hana_ctx* ctx = s->ctx;
     HANA_TRY(use_device(ctx));
-    if (uniforms_dev != s->u_raw)
-        CU_TRY(cudaMemcpyAsync(s->u_raw, uniforms_dev, sizeof(HanaUniforms) * n_frames, cudaMemcpyDeviceToDevice, ctx->stream));
     return sweep_render_common(s, model, shader_id, nullptr, enable_shadow != 0, n_frames, diffuse, normal, clear_rgba,
-                               clear_depth);
+                               clear_depth, uniforms_dev);
 }
 
 extern "C" int hana_sweep_uniforms_dev(hana_sweep* s, void** out) {
@@ -1786,7 +1871,7 @@ extern "C" int hana_sweep_stats(hana_sweep* s, int frame, HanaStats* out) {
     *out = s->last_stats;
     out->pixels_covered = px;
     if (s->stats_lazy) { /* the main pass's counters are still where it left them */
-        const Scratch& sc = s->stats_scratch ? ctx->sc2 : ctx->sc;
+        const Scratch& sc = scratch_of(ctx, s->stats_scratch);
         PassCounters c;
         uint32_t ways[TRI_COUNT_WAYS];
         CU_TRY(cudaMemcpy(&c, sc.counters, sizeof(c), cudaMemcpyDeviceToHost));

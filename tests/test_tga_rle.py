@@ -45,6 +45,20 @@ def test_parallel_model_equals_sequential_algorithm():
             assert parallel_packets(px, chunk) == ref, (trial, n, chunk)
 
 
+def test_emulated_kernels_equal_sequential_algorithm():
+    """csrc/hana_tga_core.cuh — the arithmetic the encoder's kernels are made of — compiled for the host and walked with
+    the kernels' control flow (tests/emu/emu_tga.cpp): payload byte-identical to the sequential algorithm's, the closed-form
+    byte count of every word equal to the sum over its pixels, whatever the number of threads of the structure kernel."""
+    from emu_tga_check import run
+    rng = np.random.RandomState(4)
+    for trial in range(400):
+        n = int(rng.choice([1, 2, 31, 32, 33, 127, 128, 129, 255, 256, 257, 1023, 1024, 1025, 4096, rng.randint(1, 6000)]))
+        px = crafted_stream(rng, n, trial % 5)
+        ref = sequential_packets(px)
+        for threads in (1, 5, 1024):
+            assert run(px, threads) == ref, (trial, n, threads)
+
+
 def test_sequential_model_equals_host_writer(hana, tmp_path):
     rng = np.random.RandomState(2)
     for kind in range(5):
