@@ -369,52 +369,57 @@ __global__ void __launch_bounds__(TGA_C_THREADS) tga_write_kernel(const uint32_t
         o[2] = (uint8_t)(px >> 8);
         o[3] = (uint8_t)px;
     }
-    /* every other word: a lane per pixel. What the lanes need of word g travels in six shuffles. */
+    /* every other word: a lane per pixel. What the lanes need of word g travels in seven shuffles: its e bits, its xm, the
+     * two masks and two numbers of tga_word_emit, its byte offset + neighbour bits, buffer index / column of its first pixel */
     unsigned gm = __ballot_sync(FULL, q.cls == TGA_W_GENERAL || q.cls == TGA_W_RAW);
     if (!gm) return;
     const unsigned lt_mask = (1u << lane) - 1u;
-    const uint32_t misc = (inc - cnt) | (q.eprev << 16) | (q.enext << 17) | ((q.cls == TGA_W_RAW ? 1u : 0u) << 18); /* offset in the batch <= 4096 */
+    const TgaWordEmit we = tga_word_emit(q.rec, tga_masks(q.cur, q.eprev, q.enext), w, n);
+    const uint32_t misc = (inc - cnt) | (q.eprev << 13) | (q.enext << 14) | (we.rc << 15) | (we.r0c << 22); /* offset in the batch <= 4096 */
     uint8_t* const bpay = payload + batch_offs[(size_t)f * L.nbatch + batch];
-    do {
-        const int g = __ffs((int)gm) - 1;
-        gm &= gm - 1;
-        const int wg = batch * 32 + g;
-        const int i = wg * 32 + lane;
-        const uint32_t gmisc = __shfl_sync(FULL, misc, g);
-        TgaRec rec;
-        rec.a = __shfl_sync(FULL, q.rec.a, g);
-        rec.t = __shfl_sync(FULL, q.rec.t, g);
-        rec.xm = __shfl_sync(FULL, q.rec.xm, g);
-        rec.pad = 0u;
-        uint8_t* o = bpay + (gmisc & 0xFFFFu);
+    /* the pixel of word g for this lane; the load of the NEXT word's pixels is in flight while a word is worked on */
+    auto fetch = [&](int g) -> uint32_t {
         int c2 = __shfl_sync(FULL, col, g) + lane, i2 = __shfl_sync(FULL, idx, g) + lane;
         while (c2 >= W) c2 -= W, i2 -= 2 * W; /* into the next file row = the buffer row in front */
-        unsigned inf;
-        if (gmisc & (1u << 18)) { /* the middle of a raw stretch: consecutive raw pixels (cur == 0: no shuffle needed) */
-            const int k = (tga_raw_word_idx0(rec, wg) + lane) & 127;
-            inf = 2u | ((unsigned)k << 2) | ((k == 127 || i == n - 1) ? 1u << 9 : 0u);
-        } else {
-            const TgaMasks m = tga_masks(__shfl_sync(FULL, q.cur, g), (gmisc >> 16) & 1u, (gmisc >> 17) & 1u);
-            inf = tga_lane_role(rec, m, wg, lane, n);
+        return (batch * 32 + g) * 32 + lane < n ? __ldg(src + i2) : 0u;
+    };
+    int g = __ffs((int)gm) - 1;
+    gm &= gm - 1;
+    uint32_t px = fetch(g);
+    while (true) {
+        int g_next = -1;
+        uint32_t px_next = 0;
+        if (gm) {
+            g_next = __ffs((int)gm) - 1;
+            gm &= gm - 1;
+            px_next = fetch(g_next);
         }
+        const int wg = batch * 32 + g;
+        const uint32_t gmisc = __shfl_sync(FULL, misc, g);
+        const TgaMasks m = tga_masks(__shfl_sync(FULL, q.cur, g), (gmisc >> 13) & 1u, (gmisc >> 14) & 1u);
+        TgaWordEmit e;
+        e.alone = __shfl_sync(FULL, we.alone, g);
+        e.ends = __shfl_sync(FULL, we.ends, g);
+        e.rc = (gmisc >> 15) & 127u;
+        e.r0c = (gmisc >> 22) & 127u;
+        const unsigned inf = tga_lane_emit(m, __shfl_sync(FULL, q.rec.xm, g), e, wg, lane, n);
         const unsigned role = inf & 3u, k = (inf >> 2) & 127u;
-        uint32_t px = 0;
-        if (role) px = __ldg(src + i2);
         const unsigned m1 = __ballot_sync(FULL, role == 1u), m2 = __ballot_sync(FULL, role == 2u), mh = __ballot_sync(FULL, role == 2u && k == 0u);
-        const unsigned pos = 4u * __popc(m1 & lt_mask) + 3u * __popc(m2 & lt_mask) + __popc(mh & lt_mask);
-        if (role == 1u) {
-            o[pos] = (uint8_t)(k + 128u);
-            o[pos + 1] = (uint8_t)(px >> 16);
-            o[pos + 2] = (uint8_t)(px >> 8);
-            o[pos + 3] = (uint8_t)px;
-        } else if (role == 2u) {
-            uint8_t* c = o + pos + (k == 0u ? 1u : 0u);
-            c[0] = (uint8_t)(px >> 16);
+        const unsigned pos = (gmisc & 0x1FFFu) + 4u * __popc(m1 & lt_mask) + 3u * __popc(m2 & lt_mask) + __popc(mh & lt_mask);
+        if (role) {
+            /* one path for both roles: a byte in front of the colour when the pixel ends a run packet ([k + 128]) or opens a
+             * raw packet (its header, written by the packet's last pixel, 3 k + 1 bytes in front of that pixel's colour) */
+            const bool run = role == 1u;
+            uint8_t* c = bpay + (pos + ((run || k == 0u) ? 1u : 0u));
+            c[0] = (uint8_t)(px >> 16); /* the file wants B,G,R: the buffer's u32 is R | G << 8 | B << 16 */
             c[1] = (uint8_t)(px >> 8);
             c[2] = (uint8_t)px;
-            if (inf & (1u << 9)) *(c - 3 * (int)k - 1) = (uint8_t)k; /* the packet's header, possibly in an earlier word's bytes */
+            if (run || (inf & (1u << 9))) *(c - 1 - (run ? 0 : 3 * (int)k)) = (uint8_t)(k + (run ? 128u : 0u));
         }
-    } while (gm);
+        if (g_next < 0) break;
+        g = g_next;
+        px = px_next;
+    }
 }
 
 }  // namespace hana

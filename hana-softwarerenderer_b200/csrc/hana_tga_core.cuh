@@ -317,5 +317,70 @@ TGA_HD unsigned tga_word_bytes(const TgaRec& r, const TgaMasks& m, int w, int n)
     return bytes;
 }
 
+
+/* ---- the write kernel's form of the per-pixel role. What the pixels in FRONT of a word's first T-start need of the record
+ * (they continue its stretch) is folded by the word's lane into two masks and two small numbers; with them a pixel's role
+ * follows from the word's masks alone — straight-line code, no (a, t) arithmetic per pixel (tests/emu checks it against
+ * tga_lane_role pixel by pixel). ---- */
+struct TgaWordEmit {
+    uint32_t alone; /* tails that are alone in their packet: raw, first pixel of the raw group behind */
+    uint32_t ends;  /* last pixels of run packets */
+    uint32_t rc;    /* rawidx % 128 of (virtual) pixel 0 of the continued raw part */
+    uint32_t r0c;   /* idx % 128 of (virtual) pixel 0 of the continued run part */
+};
+TGA_HD TgaWordEmit tga_word_emit(const TgaRec& r, const TgaMasks& m, int w, int n) {
+    const int base = w * 32, nv = n - base;
+    const uint32_t VM = nv >= 32 ? 0xFFFFFFFFu : (nv <= 0 ? 0u : ((1u << nv) - 1u));
+    const uint32_t G = m.cur | m.tl;
+    const uint32_t L = m.ts ? ~((m.ts & (0u - m.ts)) - 1u) : 0u; /* from the first T-start on */
+    const uint32_t C = VM & ~L;
+    const uint32_t XS = m.ts & r.xm; /* T-starts taken as the 128th pixel of the raw packet in front */
+    TgaWordEmit e;
+    e.alone = m.tl & (XS << 1);
+    e.ends = 0u;
+    e.rc = (uint32_t)base & 127u;
+    e.r0c = 0u;
+    if (C && r.a >= 0) {
+        const int r0 = r.a + (int)(r.xm & 1u);
+        e.r0c = (uint32_t)(base - r0) & 127u;
+        const uint32_t RG = G & C, tcm = m.tl & C;
+        int tt = r.t;
+        if (RG) {
+            const uint32_t j127 = (127u - e.r0c) & 127u;
+            if (j127 < 32u) e.ends = RG & (1u << j127); /* a full packet of the continued run ends here */
+            if (tcm) {
+                const int tc = tga_lo(tcm);
+                if (((e.r0c + (uint32_t)tc) & 127u) == 0u) e.alone |= tcm;
+                tt = base + tc;
+            }
+        }
+        const int y = (((tt - r0 + 1) & 127) == 1) ? 1 : 0;
+        e.rc = (uint32_t)(base - tt - 1 + y) & 127u;
+    }
+    e.ends |= m.tl & ~e.alone;
+    return e;
+}
+/* same result as tga_lane_role; `e` is the word's, j the pixel */
+TGA_HD unsigned tga_lane_emit(const TgaMasks& m, uint32_t xm, const TgaWordEmit& e, int w, int j, int n) {
+    const int i = w * 32 + j;
+    const uint32_t bit = 1u << j, upto = 0xFFFFFFFFu >> (31 - j);
+    const uint32_t XS = m.ts & xm;
+    const uint32_t ts_upto = m.ts & upto, tl_upto = m.tl & upto;
+    const bool is_end = (e.ends & bit) != 0u;
+    const bool is_raw = !is_end && (((~(m.cur | m.tl) | XS | e.alone) & bit) != 0u);
+    const int ha = tga_hi(ts_upto | 1u), ht = tga_hi(tl_upto | 1u); /* 0 when there is none: unused then */
+    /* run packet end: k = idx % 128 */
+    const int k_end = ts_upto ? j - ha - (int)((xm >> ha) & 1u) : (int)((e.r0c + (uint32_t)j) & 127u);
+    /* raw: k = rawidx % 128 */
+    int k_raw = tl_upto ? j - ht - 1 + (int)((e.alone >> ht) & 1u) : (int)((e.rc + (uint32_t)j) & 127u);
+    if (e.alone & bit) k_raw = 0;
+    if (XS & bit) k_raw = 127;
+    const bool last = k_raw == 127 || i == n - 1 || ((m.se & bit) && k_raw != 126);
+    unsigned out = 0u;
+    if (is_raw) out = 2u | ((unsigned)k_raw << 2) | (last ? 1u << 9 : 0u);
+    if (is_end) out = 1u | ((unsigned)k_end << 2);
+    return i < n ? out : 0u;
+}
+
 }  // namespace hana
 #endif /* HANA_TGA_CORE_CUH */

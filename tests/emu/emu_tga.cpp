@@ -54,6 +54,9 @@ size_t emu_tga_payload(const uint32_t* px, int n, int threads, uint8_t* out) {
         for (int j = 0; j < 32; j++) c += tga_role_bytes(tga_lane_role(R[w], m, w, j, n));
         if (c != cnt[w]) return (size_t)-1 - (size_t)w; // closed form and per-pixel roles disagree
         if (cls[w] != TGA_W_GENERAL && tga_closed_word_bytes(cls[w], R[w], w) != c) return (size_t)-1 - (size_t)w;
+        const TgaWordEmit we = tga_word_emit(R[w], m, w, n); // the write kernel's form of the role, pixel by pixel
+        for (int j = 0; j < 32; j++)
+            if (tga_lane_emit(m, R[w].xm, we, w, j, n) != tga_lane_role(R[w], m, w, j, n)) return (size_t)-1 - (size_t)w;
     }
     // ---- scan + tga_write_kernel
     size_t off = 0;
