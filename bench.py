@@ -608,6 +608,9 @@ def main():
                                "note": "SURVEY.md §8(d) bytes of the whole frame (both passes) over the step time per GPU"},
             "kernel_ms_per_step": {k: v / max(prof_steps, 1) for k, v in kernel_ms.items()},
             "kernel_ms_sampled_steps": prof_steps,
+            "kernel_ms_note": "CUDA-event time per kernel class. Submissions are pipelined: the binning kernels (begin, setup, scan, fill) "
+                              "of step k+1 are queued on side streams beside the rasterisers of step k, so their event times include "
+                              "waiting for SM slots and the classes do not add up to the step; HANA_NO_PIPELINE=1 gives the serial breakdown",
             "cpu_baseline": cpu,
         }
         if extras:
@@ -719,6 +722,33 @@ def run_extras(hana, ctx, peak, assets):
                                   "frames_per_s_batched": F / (ms * 1e-3),
                                   "single_frame_host_call_ms": single, "single_frame_fps": 1e3 / single["median"]}
     af = hana.load_bundled(SCENE, assets, NORMAL_PASS)
+    # optional static-light shadow-map reuse (off by default, never the headline): the headline workload
+    # through hana_sweep_render with ONE ShadowShader pass per batch instead of one per frame, frames byte-identical
+    try:
+        F = 256
+        objs = af.upload(ctx)
+        arr = hana.orbit_sweep_uniforms(W, H, 0, F, frames_per_turn=ORBIT)
+        sw = ctx.sweep(W, H, F)
+        res = {}
+        for reuse in (False, True):
+            sw.set_shadow_reuse(reuse)
+            for _ in range(2):
+                sw.render(objs[0], hana.BLINN, arr, objs[1], objs[2])
+            ctx.sync()
+            res[reuse] = sw.checksums(F)
+            ctx.timer_start()
+            for _ in range(4):
+                sw.render(objs[0], hana.BLINN, arr, objs[1], objs[2])
+            res[("fps", reuse)] = 4 * F / (ctx.timer_stop() * 1e-3)
+        out["shadow_reuse"] = {"config": "headline frames, %d per submission through hana_sweep_render, hana_sweep_set_shadow_reuse on: one "
+                                         "shadow map per batch (the orbit leaves light_vp and model unchanged, scene.h:69)" % F,
+                               "frames_per_s": res[("fps", True)], "frames_per_s_per_frame_passes": res[("fps", False)],
+                               "frames_identical": bool(np.array_equal(res[True], res[False])),
+                               "note": "optional algorithmic change; the headline `value` renders the ShadowShader pass for every frame as the reference does"}
+        for o in (sw,) + tuple(objs):
+            o.close()
+    except Exception as e:  # an extra: never fail the bench for it
+        out["shadow_reuse"] = {"error": str(e)}
     lat["hana_draw_model_host_c1_800x600_blinn_noshadow"] = host_call_ms(af, hana.BLINN, 800, 600, False)
     lat["hana_draw_model_host_c2_1920x1080_blinn_shadow"] = host_call_ms(af, hana.BLINN, 1920, 1080, True)
     out["latency_ms"] = dict(lat, note="wall clock of ONE synchronous hana_draw_model_host call (Level-2 boundary, INTEGRATION.md): "

@@ -137,6 +137,7 @@ def load():
         "hana_sweep_encode_tga": [vp, i, i],
         "hana_sweep_fetch_tga": [vp, vp, C.c_size_t, vp, vp],
         "hana_sweep_set_bands": [vp, i, i, i, i],
+        "hana_sweep_set_shadow_reuse": [vp, i],
         "hana_sweep_render_pass": [vp, i, vp, i, vp, i, vp, vp, vp, f],
         "hana_sweep_shadow_ptrs": [vp, C.POINTER(vp), C.POINTER(i), C.POINTER(C.c_size_t)],
         "hana_sweep_render_pass_async": [vp, i, vp, i, vp, i, vp, vp, vp, f],
@@ -410,6 +411,11 @@ class Sweep:
         clr = (C.c_uint8 * 4)(*clear_rgba)
         _ck(self.ctx.L.hana_sweep_render_dev(self.h, model.h, shader, dev, int(bool(enable_shadow)), n_frames, _h(diffuse),
                                              _h(normal), clr, float(clear_depth)))
+
+    def set_shadow_reuse(self, enable=True):
+        """Optional (off by default): a batch whose frames all carry the same light_vp and model matrices renders ONE
+        shadow map for all of them (scene.h:73-88 with a static light); frames are byte-identical either way."""
+        _ck(self.ctx.L.hana_sweep_set_shadow_reuse(self.h, int(bool(enable))))
 
     # -- one frame split by screen tiles over several GPUs (SURVEY.md §8e) --
     def set_bands(self, shadow=(0, 0), main=(0, 0)):

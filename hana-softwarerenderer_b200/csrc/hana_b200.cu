@@ -191,6 +191,9 @@ struct hana_sweep {
     cudaEvent_t ev_render, ev_copy;
     bool copy_in_flight;
     int band[2][2];                /* tile rows [first, first+count) of the shadow / main pass; count 0 = all (hana_sweep_set_bands) */
+    bool shadow_reuse = false;     /* hana_sweep_set_shadow_reuse */
+    bool shadow_shared = false;    /* the last batch rendered ONE shadow map for all its frames */
+    uint64_t shadow_shared_batches = 0;
     uint8_t* present_buf;          /* device: presented frames (hana_sweep_present) */
     size_t present_cap;
     /* RLE TGA files made on the device (hana_sweep_encode_tga / hana_sweep_fetch_tga) */
@@ -223,6 +226,7 @@ struct hana_sweep {
         float clear_depth = 0.f;
         uint32_t tri_cap = 0, pool_cap = 0;
         int slot = 0;
+        bool share_shadow = false;
     } pending;
 };
 
@@ -1266,8 +1270,10 @@ extern "C" int hana_sweep_destroy(hana_sweep* s) {
 enum { SWEEP_PASS_SHADOW = 1, SWEEP_PASS_MAIN = 2, SWEEP_PASS_BOTH = 3 };
 static int sweep_render_passes(hana_sweep* s, const hana_model* model, int shader_id, int enable_shadow, int n_frames,
                                const hana_texture* diffuse, const hana_texture* normal, const uint8_t clear_rgba[4],
-                               float clear_depth, bool lazy, int passes = SWEEP_PASS_BOTH, int pipe_parity = -1) {
+                               float clear_depth, bool lazy, int passes = SWEEP_PASS_BOTH, int pipe_parity = -1, bool share_shadow = false) {
     hana_ctx* ctx = s->ctx;
+    s->shadow_shared = share_shadow && enable_shadow && passes == SWEEP_PASS_BOTH;
+    if (s->shadow_shared) s->shadow_shared_batches++;
     const bool pipe = pipe_parity >= 0; /* lazy, both passes: binned on bin_stream / side_stream with this parity's scratch sets */
     PassCounters cnt[2];
     memset(cnt, 0, sizeof(cnt));
@@ -1276,7 +1282,7 @@ static int sweep_render_passes(hana_sweep* s, const hana_model* model, int shade
         PassDesc d;
         d.shader = HANA_SHADER_SHADOW;
         d.mode = MODE_SHADOW_R8;
-        d.n_frames = n_frames;
+        d.n_frames = s->shadow_shared ? 1 : n_frames; /* every frame's light and model are frame 0's: one map */
         d.W = s->w;
         d.H = s->h;
         d.model = model;
@@ -1344,7 +1350,7 @@ static int sweep_render_passes(hana_sweep* s, const hana_model* model, int shade
         d.shadow.h = s->h;
         d.shadow.pitch = s->shadow_pitch;
         d.shadow.stride = 1;
-        d.shadow_frame_stride = s->shadow_frame_bytes;
+        d.shadow_frame_stride = s->shadow_shared ? 0 : s->shadow_frame_bytes;
     }
     d.prof_kind = PROF_RASTER_MAIN;
     d.counters_out = &cnt[1];
@@ -1437,7 +1443,7 @@ static int sweep_verify(hana_sweep* s) {
     HANA_TRY(grow_scratch_for(ctx, need));
     s->rerender_count++;
     return sweep_render_passes(s, pd.model, pd.shader, pd.enable_shadow, pd.n_frames, pd.diffuse, pd.normal, pd.clear_rgba,
-                               pd.clear_depth, false);
+                               pd.clear_depth, false, SWEEP_PASS_BOTH, -1, pd.share_shadow);
 }
 
 static int sweep_render_common(hana_sweep* s, const hana_model* model, int shader_id, const HanaUniforms* host_uniforms,
@@ -1487,8 +1493,16 @@ static int sweep_render_common(hana_sweep* s, const hana_model* model, int shade
     HANA_TRY(upload_uniforms(ctx, host_uniforms, n_frames, s->u_raw, s->u_dev, ust));
     CU_TRY(cudaMemsetAsync(s->overflow, 0, sizeof(OverflowRecord), ust));
     const bool dirty_before = ctx->serial_dirty;
+    /* static light (hana_sweep_set_shadow_reuse): the ShadowShader pass reads light_vp * model only (IShader.cpp:170) */
+    bool share = false;
+    if (s->shadow_reuse && enable_shadow && host_uniforms && n_frames > 1) {
+        share = true;
+        for (int i = 1; i < n_frames && share; i++)
+            share = memcmp(host_uniforms[i].light_vp, host_uniforms[0].light_vp, sizeof(host_uniforms[0].light_vp)) == 0 &&
+                    memcmp(host_uniforms[i].model, host_uniforms[0].model, sizeof(host_uniforms[0].model)) == 0;
+    }
     HANA_TRY(sweep_render_passes(s, model, shader_id, enable_shadow, n_frames, diffuse, normal, clear_rgba, clear_depth, true,
-                                 SWEEP_PASS_BOTH, parity));
+                                 SWEEP_PASS_BOTH, parity, share));
     if (pipe) ctx->serial_dirty = dirty_before;
     const int slot = s->next_slot;
     s->next_slot = (slot + 1) % (hana_sweep::CHECK_RING + 1);
@@ -1510,6 +1524,13 @@ static int sweep_render_common(hana_sweep* s, const hana_model* model, int shade
     pd.normal = normal;
     memcpy(pd.clear_rgba, clear_rgba, 4);
     pd.clear_depth = clear_depth;
+    pd.share_shadow = share;
+    return HANA_OK;
+}
+
+extern "C" int hana_sweep_set_shadow_reuse(hana_sweep* s, int enable) {
+    if (!s) return fail(HANA_E_INVALID, "sweep is NULL");
+    s->shadow_reuse = enable != 0;
     return HANA_OK;
 }
 

@@ -256,6 +256,16 @@ HANA_API int hana_sweep_stats(hana_sweep* s, int frame, HanaStats* out); /* sync
  * loop does). Waits for everything queued so far. 0 = no frame handed out so far was incomplete. */
 HANA_API int hana_sweep_overflow_count(hana_sweep* s, uint64_t* out);
 
+/* Optional, OFF by default ("shadow-map reuse when the light is static — algorithmic change"): the
+ * ShadowShader pass of DrawModel::draw (scene.h:73-88) reads nothing but light_vp_matrix * model_matrix (IShader.cpp:170),
+ * which an orbiting camera does not change (scene.h:69: the light looks at the camera's fixed TARGET). With reuse enabled,
+ * a hana_sweep_render batch whose frames all carry bit-identical `light_vp` and `model` renders ONE shadow map and every
+ * frame's BlinnShader/NormalMapShader pass reads it; the frames are byte-identical to those of the per-frame passes
+ * (the reference renders the same map again every frame, then clears it, scene.h:94-98). A batch whose frames differ in
+ * either matrix is rendered pass by pass as always. hana_sweep_render_dev (uniforms already on the device, nothing to
+ * compare on the host) ignores the setting. bench.py reports it as an extra key, never as the headline. */
+HANA_API int hana_sweep_set_shadow_reuse(hana_sweep* s, int enable);
+
 /* --- one frame split by screen tiles over several GPUs (BASELINE.json north_star, optional mode) --
  * The frame's 16x16 tiles are dealt to the GPUs in bands of tile rows. Geometry is replicated; each GPU rasterises
  * only the tiles of its band, per pass. Replaces nothing in the reference (it has one thread); the per-GPU work is

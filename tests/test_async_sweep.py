@@ -78,3 +78,30 @@ def test_two_rings_with_overlapped_copies(hana, ctx):
         assert np.array_equal(got[k], want[k]), k
     for o in rings + [model, dtex, ntex] + pins:
         o.close()
+
+
+def test_static_light_shadow_reuse_gives_identical_frames(hana, ctx):
+    """hana_sweep_set_shadow_reuse (optional): an orbit batch (the light looks at the camera's fixed target:
+    light_vp and model are the same in every frame, scene.h:69) rendered with ONE shadow map equals the batch rendered with
+    a ShadowShader pass per frame, bit for bit; a batch whose light moves is rendered pass by pass whatever the setting."""
+    W, Hh, F = 640, 360, 6
+    scene = hana.synthetic_scene("blob")
+    model, dtex, ntex = scene.upload(ctx)
+    orbit = hana.orbit_sweep_uniforms(W, Hh, 3, F, frames_per_turn=32)
+    moving = hana.orbit_sweep_uniforms(W, Hh, 3, F, frames_per_turn=32)
+    moving[4].light_vp[3] += 0.05  # one frame's light elsewhere
+    sw = ctx.sweep(W, Hh, F)
+    for batch in (orbit, moving):
+        sw.set_shadow_reuse(False)
+        sw.render(model, hana.BLINN, batch, dtex, ntex)
+        want = [sw.download(k) for k in range(F)]
+        l0 = ctx.launches
+        sw.set_shadow_reuse(True)
+        sw.render(model, hana.BLINN, batch, dtex, ntex)
+        for k in range(F):
+            col, dep = sw.download(k)
+            assert np.array_equal(col, want[k][0]) and np.array_equal(dep.view(np.uint32), want[k][1].view(np.uint32)), k
+        assert ctx.launches > l0
+    assert sw.overflow_count() == 0
+    for o in (sw, model, dtex, ntex):
+        o.close()
