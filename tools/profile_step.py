@@ -20,6 +20,7 @@ def main():
     ap.add_argument("--scene", default="african_head")
     ap.add_argument("--shader", default="BLINN")
     ap.add_argument("--size", default="1920x1080")
+    ap.add_argument("--tga", action="store_true", help="also encode the frames as RLE TGA files (hana_sweep_encode_tga) inside the profiled region")
     a = ap.parse_args()
     import torch
     hana = ge.load_package()
@@ -32,10 +33,14 @@ def main():
     shader = getattr(hana, a.shader)
     for _ in range(3):
         sw.render(model, shader, arr, dtex, ntex)
+        if a.tga:
+            assert ctx.L.hana_sweep_encode_tga(sw.h, 0, a.frames) == 0
         ctx.sync()
     torch.cuda.synchronize()
     torch.cuda.profiler.start()
     sw.render(model, shader, arr, dtex, ntex)
+    if a.tga:
+        assert ctx.L.hana_sweep_encode_tga(sw.h, 0, a.frames) == 0
     ctx.sync()
     torch.cuda.synchronize()
     torch.cuda.profiler.stop()
