@@ -360,19 +360,27 @@ __global__ void __launch_bounds__(TGA_C_THREADS) tga_write_kernel(const uint32_t
         col = w * 32 - row * W;
         idx = (H - 1 - row) * W + col;
     }
-    /* a word in the middle of a run: at most one packet ends in it, [255, B, G, R]; all its pixels are equal */
-    if (q.cls == TGA_W_RUN && tga_run_word_end(q.rec, w) < 32) {
-        const uint32_t px = __ldg(src + idx);
-        uint8_t* o = payload + woff;
-        o[0] = 255;
-        o[1] = (uint8_t)(px >> 16); /* the file wants B,G,R: the buffer's u32 is R | G << 8 | B << 16 */
-        o[2] = (uint8_t)(px >> 8);
-        o[3] = (uint8_t)px;
-    }
+    /* a word in the middle of a run: at most one packet ends in it, [255, B, G, R]; all its pixels are equal. The pixel is
+     * requested here and stored behind the loop over the other words, so nobody waits for it. */
+    const bool run_end = q.cls == TGA_W_RUN && tga_run_word_end(q.rec, w) < 32;
+    uint32_t run_px = 0;
+    if (run_end) run_px = __ldg(src + idx);
+    auto store_run_end = [&]() {
+        if (run_end) {
+            uint8_t* o = payload + woff;
+            o[0] = 255;
+            o[1] = (uint8_t)(run_px >> 16); /* the file wants B,G,R: the buffer's u32 is R | G << 8 | B << 16 */
+            o[2] = (uint8_t)(run_px >> 8);
+            o[3] = (uint8_t)run_px;
+        }
+    };
     /* every other word: a lane per pixel. What the lanes need of word g travels in seven shuffles: its e bits, its xm, the
      * two masks and two numbers of tga_word_emit, its byte offset + neighbour bits, buffer index / column of its first pixel */
     unsigned gm = __ballot_sync(FULL, q.cls == TGA_W_GENERAL || q.cls == TGA_W_RAW);
-    if (!gm) return;
+    if (!gm) {
+        store_run_end();
+        return;
+    }
     const unsigned lt_mask = (1u << lane) - 1u;
     const TgaWordEmit we = tga_word_emit(q.rec, tga_masks(q.cur, q.eprev, q.enext), w, n);
     const uint32_t misc = (inc - cnt) | (q.eprev << 13) | (q.enext << 14) | (we.rc << 15) | (we.r0c << 22); /* offset in the batch <= 4096 */
@@ -420,6 +428,7 @@ __global__ void __launch_bounds__(TGA_C_THREADS) tga_write_kernel(const uint32_t
         g = g_next;
         px = px_next;
     }
+    store_run_end();
 }
 
 }  // namespace hana

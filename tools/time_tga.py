@@ -37,8 +37,7 @@ for (W, H, F) in CASES:
         ctx.sync()
         ms_fetch = (time.perf_counter() - t0) * 1e3
         best = min(best, ms_enc)
-    chunks = (W * H + 4095) // 4096
-    print("%dx%d F=%d: encode %.3f ms = %.2f us/frame = %.2f us per chunk of the chain (%d chunks); fetch %.3f ms, %.0f bytes/frame, %.1f GB/s" %
-          (W, H, F, best, best * 1e3 / F, best * 1e3 / chunks, chunks, ms_fetch, offs[F] / F, offs[F] / ms_fetch / 1e6))
+    print("%dx%d F=%d: encode %.3f ms = %.2f us/frame; fetch %.3f ms, %.0f bytes/frame, %.1f GB/s" %
+          (W, H, F, best, best * 1e3 / F, ms_fetch, offs[F] / F, offs[F] / ms_fetch / 1e6))
     pin.close()
     sw.close()
