@@ -66,6 +66,8 @@ struct Scratch {
     size_t tile_arr_cap = 0;
     unsigned long long* vis = nullptr; /* visibility buffer of the micro-triangle path (dense meshes only): n_frames * W * H */
     size_t vis_cap = 0;
+    uint32_t* group_listed = nullptr;  /* with a visibility buffer: n_frames * ceil(tri_cap / 32) flags (PassParams) */
+    size_t group_cap = 0;
     float4* tile_recs = nullptr; /* pool of raster records: 4 float4 each */
     size_t pool_cap = 0;         /* float4 elements */
     uint4* work = nullptr;
@@ -351,7 +353,7 @@ extern "C" int hana_ctx_destroy(hana_ctx* ctx) {
     for (Scratch* sp : {&ctx->sc, &ctx->sc2, &ctx->sc3, &ctx->sc4}) {
         Scratch& s = *sp;
         cudaFree(s.tri_rec); cudaFree(s.tri_attr); cudaFree(s.tri_bbox); cudaFree(s.tri_count); cudaFree(s.tile_arrays);
-        cudaFree(s.tile_recs); cudaFree(s.work); cudaFree(s.counters); cudaFreeHost(s.counters_host); cudaFree(s.vis);
+        cudaFree(s.tile_recs); cudaFree(s.work); cudaFree(s.counters); cudaFreeHost(s.counters_host); cudaFree(s.vis); cudaFree(s.group_listed);
     }
     cudaStreamDestroy(ctx->side_stream);
     cudaStreamDestroy(ctx->bin_stream);
@@ -844,6 +846,8 @@ static int run_pass(hana_ctx* ctx, const PassDesc& d) {
          * draws: the target's existing depth takes part there. */
         const bool use_vis = d.mode != MODE_RMW && !d.setup_only && (size_t)nfaces * 16 >= (size_t)d.W * d.H && !getenv("HANA_NO_VIS");
         if (use_vis) HANA_TRY(grow(&sc.vis, &sc.vis_cap, (size_t)d.W * d.H * d.n_frames, ctx));
+        const size_t n_groups = ((size_t)tri_cap + 31) / 32 * d.n_frames;
+        if (use_vis) HANA_TRY(grow(&sc.group_listed, &sc.group_cap, n_groups, ctx));
         HANA_TRY(grow(&sc.work, &sc.work_cap, tiles_total, ctx));
         if (!sc.tile_recs || sc.pool_cap / 4 < ctx->pool_hint)
             HANA_TRY(grow(&sc.tile_recs, &sc.pool_cap, std::max<size_t>(std::max<size_t>(tri_total * 2, 65536), ctx->pool_hint) * 4, ctx));
@@ -871,6 +875,7 @@ static int run_pass(hana_ctx* ctx, const PassDesc& d) {
         p.tile_micro = sc.tile_arrays + 2 * tiles_pad_total;
         p.tile_offset = sc.tile_arrays + 3 * tiles_pad_total;
         p.vis = use_vis ? sc.vis : nullptr;
+        p.group_listed = use_vis ? sc.group_listed : nullptr;
         p.tile_rows = tile_rows;
         p.tile_pad = tile_rows * 32;
         p.tile_recs = sc.tile_recs;
@@ -885,6 +890,7 @@ static int run_pass(hana_ctx* ctx, const PassDesc& d) {
         CU_TRY(cudaMemsetAsync(sc.tri_count, 0, sizeof(uint32_t) * d.n_frames * (TRI_COUNT_WAYS + 1), st));
         CU_TRY(cudaMemsetAsync(sc.tile_arrays, 0, sizeof(uint32_t) * 3 * tiles_pad_total, st));
         if (use_vis) CU_TRY(cudaMemsetAsync(sc.vis, 0xFF, sizeof(unsigned long long) * (size_t)d.W * d.H * d.n_frames, st));
+        if (use_vis) CU_TRY(cudaMemsetAsync(sc.group_listed, 0, sizeof(uint32_t) * n_groups, st));
 
         cudaEvent_t ea, eb;
         if (nfaces > 0) {

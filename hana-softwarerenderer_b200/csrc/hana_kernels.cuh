@@ -43,9 +43,9 @@ constexpr int SETUP_THREADS = 256;
 #define HANA_SETUP_CTAS 3 /* resident CTAs per SM setup_kernel is compiled for */
 #endif
 #ifndef HANA_MICRO_EXTENT
-#define HANA_MICRO_EXTENT 3
+#define HANA_MICRO_EXTENT 5 /* configs[3], ms per frame: 3 -> 3.37 (793 k list records left), 4 -> 3.16 (18 k), 5 -> 3.13 (172), 8 -> 3.09 */
 #endif
-constexpr int MICRO_EXTENT = HANA_MICRO_EXTENT; /* a triangle whose pixel range is at most this many pixels on a side takes the visibility-buffer path */
+constexpr int MICRO_EXTENT = HANA_MICRO_EXTENT; /* a triangle of a dense mesh whose pixel range is at most this many pixels on a side takes the visibility-buffer path (at most MICRO_EXTENT^2 pixel tests by its thread in setup_kernel) instead of the tile lists */
 constexpr int TRI_COUNT_WAYS = 32;   /* per-frame statistics counters: one atomic per warp, spread so that they do not queue on one address */
 constexpr uint32_t DEAD_BBY = 0x0000FFFFu; /* bby of a slot that holds no triangle (y0 = 0xFFFF > y1 = 0: an empty range for every consumer) */
 constexpr int SCAN_THREADS = 1024;
@@ -104,6 +104,9 @@ struct PassParams {
     uint32_t* tile_micro;  /* [n_frames][tile_pad], tile_slot(): != 0 where the visibility buffer holds fragments of the tile */
     unsigned long long* vis; /* optional [n_frames][H][W]: (depth bits << 32 | ~order key) of the best micro-triangle fragment
                                 per pixel, all ones where there is none (dense meshes: see setup_kernel) */
+    uint32_t* group_listed;  /* optional (passes with a visibility buffer) [n_frames][(tri_cap + 31) / 32]: != 0 where one of the 32
+                                slots holds a triangle the pair kernels must list; a dense mesh is almost all micro-triangles,
+                                and their warps leave at once instead of reading 32 pixel ranges to find nothing */
     int tile_pad, tile_rows; /* tile_pad = 32 * tile_rows >= n_tiles */
     float4* tile_recs;    /* pool of raster records (4 x float4 each), grouped per (frame, tile) */
     uint32_t pool_cap;    /* in records */
@@ -288,6 +291,7 @@ __device__ __noinline__ void setup_clipped(const PassParams& p, int f, int face,
         if (slot < p.tri_cap) {
             store_triangle<SHADER>(p, f, slot, r, a, b, c);
             count_single_tile(p, f, r);
+            if (p.group_listed) p.group_listed[(size_t)f * ((p.tri_cap + 31u) >> 5) + (slot >> 5)] = 1u;
         }
     }
 }
@@ -326,11 +330,12 @@ __global__ void __launch_bounds__(SETUP_THREADS, HANA_SETUP_CTAS) setup_kernel(c
      * samples on a 10 M-face mesh). A face that emits nothing here (culled, degenerate, or clipped: its fan lives in
      * slots >= nfaces) marks its slot empty; the pair kernels skip it by its empty pixel range. */
     int key = -1;
+    bool listed = false; /* the pair kernels have to look at this slot */
     if (face < p.nfaces && (uint32_t)face < p.tri_cap) {
         if (emit) {
             store_triangle<SHADER>(p, f, (uint32_t)face, r, v, v + V2F_N, v + 2 * V2F_N);
-            /* Micro-triangles (pixel range at most 3x3: a dense mesh has millions, BASELINE.json configs[3]) do not go
-             * through the tile lists, where the tile's warp would walk them one by one. Their <= 9 pixels are tested right
+            /* Micro-triangles (pixel range at most MICRO_EXTENT on a side: a dense mesh has millions, BASELINE.json configs[3]) do not go
+             * through the tile lists, where the tile's warp would walk them one by one. Their pixels are tested right
              * here with the scalar statement of the coverage / weight / depth arithmetic (hana_core.cuh: the bits the tile
              * rasteriser's packed form produces) and resolved with one 64-bit atomicMin per covered pixel on the
              * visibility buffer: smallest depth first, then the largest order key (graphics.cpp:359 in submission order).
@@ -348,17 +353,23 @@ __global__ void __launch_bounds__(SETUP_THREADS, HANA_SETUP_CTAS) setup_kernel(c
                         if (!(z == z)) continue; /* a NaN depth never wins */
                         atomicMin(p.vis + ((size_t)f * p.H + y) * p.W + x,
                                   ((unsigned long long)__float_as_uint(z) << 32) | (unsigned long long)(0xFFFFFFFFu - r.key));
-                        p.tile_micro[(size_t)f * p.tile_pad + tile_slot(p, (y >> 4) * p.tiles_x + (x >> 4))] = 1u;
+                        uint32_t* tm = p.tile_micro + (size_t)f * p.tile_pad + tile_slot(p, (y >> 4) * p.tiles_x + (x >> 4));
+                        if (*tm == 0u) *tm = 1u; /* millions of fragments, thousands of tiles: a (possibly stale) read instead of a store */
                     }
                 }
                 /* not listed: the pair kernels skip a record whose pixel range is empty */
                 p.tri_bbox[(size_t)f * p.tri_cap + (uint32_t)face] = make_uint2(0u, DEAD_BBY);
             } else {
                 key = single_tile_slot(p, r);
+                listed = true;
             }
         } else {
             p.tri_bbox[(size_t)f * p.tri_cap + (uint32_t)face] = make_uint2(0u, DEAD_BBY);
         }
+    }
+    if (p.group_listed) { /* warp-uniform */
+        const unsigned any = __ballot_sync(0xFFFFFFFFu, listed);
+        if (lane == 0 && any && (uint32_t)face < p.tri_cap) p.group_listed[(size_t)f * ((p.tri_cap + 31u) >> 5) + ((uint32_t)face >> 5)] = 1u;
     }
     const unsigned live = __ballot_sync(0xFFFFFFFFu, emit);
     if (lane == 0 && live) atomicAdd(p.tri_count + (size_t)f * TRI_COUNT_WAYS + (blockIdx.x & (TRI_COUNT_WAYS - 1)), (uint32_t)__popc(live));
@@ -460,6 +471,7 @@ __global__ void __launch_bounds__(256) pairs_kernel(PassParams p) {
     uint32_t n = (uint32_t)p.nfaces + p.tri_extra[f];      /* slots in use */
     if (n > p.tri_cap) n = p.tri_cap;
     if ((i & ~31u) >= n) return;                            /* whole warp past the end */
+    if (p.group_listed && p.group_listed[(size_t)f * ((p.tri_cap + 31u) >> 5) + (i >> 5)] == 0u) return; /* nothing to list in these 32 slots */
     if (FILL && p.counters->pool_used > p.pool_cap) return; /* host re-runs the pass with a larger pool */
     const float4* warp_rec = p.tri_rec + ((size_t)f * p.tri_cap + (i & ~31u)) * 4;
     int tx0 = 0, ty0 = 0, ntx = 1, nt = 0;

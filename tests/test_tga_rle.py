@@ -103,7 +103,7 @@ def test_device_files_of_crafted_frames(hana, ctx, tmp_path):
     import torch
     from hana_softwarerenderer_b200.sharding import device_plane_tensor
     rng = np.random.RandomState(3)
-    for (W, Hh) in ((640, 96), (1000, 37), (128, 128), (4099, 5)):
+    for (W, Hh) in ((640, 96), (1000, 37), (128, 128), (4099, 5), (1, 1), (3, 7), (31, 1), (33, 2), (127, 3), (132, 9), (2048, 2)):
         F = 10
         sw = ctx.sweep(W, Hh, F)
         cptr, _, stride = sw.device_planes()
