@@ -45,6 +45,7 @@ constexpr int SETUP_THREADS = 256;
 #ifndef HANA_MICRO_EXTENT
 #define HANA_MICRO_EXTENT 5 /* configs[3], ms per frame: 3 -> 3.37 (793 k list records left), 4 -> 3.16 (18 k), 5 -> 3.13 (172), 8 -> 3.09 */
 #endif
+static_assert(HANA_MICRO_EXTENT >= 1 && HANA_MICRO_EXTENT <= 16, "a micro-triangle's pixel range must fit 2 x 2 tiles");
 constexpr int MICRO_EXTENT = HANA_MICRO_EXTENT; /* a triangle of a dense mesh whose pixel range is at most this many pixels on a side takes the visibility-buffer path (at most MICRO_EXTENT^2 pixel tests by its thread in setup_kernel) instead of the tile lists */
 constexpr int TRI_COUNT_WAYS = 32;   /* per-frame statistics counters: one atomic per warp, spread so that they do not queue on one address */
 constexpr uint32_t DEAD_BBY = 0x0000FFFFu; /* bby of a slot that holds no triangle (y0 = 0xFFFF > y1 = 0: an empty range for every consumer) */
@@ -342,6 +343,8 @@ __global__ void __launch_bounds__(SETUP_THREADS, HANA_SETUP_CTAS) setup_kernel(c
              * The tile rasteriser starts from that buffer and recomputes the winner's weights when it shades. */
             const int x0 = (int)(r.bbx & 0xFFFFu), x1 = (int)(r.bbx >> 16), y0 = (int)(r.bby & 0xFFFFu), y1 = (int)(r.bby >> 16);
             if (p.vis && x1 - x0 < MICRO_EXTENT && y1 - y0 < MICRO_EXTENT && r.uz < 0.f) {
+                uint32_t touched = 0; /* tiles (at most 2 x 2: MICRO_EXTENT <= 16) that got a fragment: bit (ty - ty0) * 2 + (tx - tx0) */
+                const int tx_o = x0 >> 4, ty_o = y0 >> 4;
                 for (int y = y0; y <= y1; y++) {
                     if ((y >> 4) < p.band_y0 || (y >> 4) >= p.band_y1) continue;
                     for (int x = x0; x <= x1; x++) {
@@ -353,10 +356,13 @@ __global__ void __launch_bounds__(SETUP_THREADS, HANA_SETUP_CTAS) setup_kernel(c
                         if (!(z == z)) continue; /* a NaN depth never wins */
                         atomicMin(p.vis + ((size_t)f * p.H + y) * p.W + x,
                                   ((unsigned long long)__float_as_uint(z) << 32) | (unsigned long long)(0xFFFFFFFFu - r.key));
-                        uint32_t* tm = p.tile_micro + (size_t)f * p.tile_pad + tile_slot(p, (y >> 4) * p.tiles_x + (x >> 4));
-                        if (*tm == 0u) *tm = 1u; /* millions of fragments, thousands of tiles: a (possibly stale) read instead of a store */
+                        touched |= 1u << ((((y >> 4) - ty_o) << 1) | ((x >> 4) - tx_o));
                     }
                 }
+                /* one flag store per touched tile and triangle, behind the loop: nothing in the loop waits for memory */
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+                    if ((touched >> k) & 1u) p.tile_micro[(size_t)f * p.tile_pad + tile_slot(p, (ty_o + (k >> 1)) * p.tiles_x + tx_o + (k & 1))] = 1u;
                 /* not listed: the pair kernels skip a record whose pixel range is empty */
                 p.tri_bbox[(size_t)f * p.tri_cap + (uint32_t)face] = make_uint2(0u, DEAD_BBY);
             } else {
