@@ -803,7 +803,9 @@ __global__ void __launch_bounds__(RW_THREADS, ShaderAttrs<SHADER>::LIT ? HANA_OC
     uint32_t i_next = 0;
     uint4 e_cur = make_uint4(WORK_INVALID, 0u, 0u, 0u);
     if (lane == 0) {
-        const uint32_t i0 = atomicAdd(&p.counters->work_cursor, 2u);
+        /* the first two items of every warp are its own by position (the queue's cursor counts from behind them): no 3 552
+         * atomics on one address before the first tile of a launch (-0.035 ms per 1024-frame step) */
+        const uint32_t i0 = 2u * (blockIdx.x * RW_WARPS + wid);
         e_cur = fetch_work(p, i0, n_work);
         i_next = i0 + 1u;
     }
@@ -823,7 +825,7 @@ __global__ void __launch_bounds__(RW_THREADS, ShaderAttrs<SHADER>::LIT ? HANA_OC
         uint32_t i_nn = 0, clr_base = 0;
         if (lane == 0) {
             e_nxt = fetch_work(p, i_next, n_work);
-            i_nn = atomic_add_async(&p.counters->work_cursor, 1u);
+            i_nn = atomic_add_async(&p.counters->work_cursor, 1u) + 2u * gridDim.x * RW_WARPS;
             if (MODE != MODE_RMW && !clear_done) clr_base = atomic_add_async(&p.counters->clear_cursor, 1u);
         }
 
