@@ -105,3 +105,59 @@ def test_static_light_shadow_reuse_gives_identical_frames(hana, ctx):
     assert sw.overflow_count() == 0
     for o in (sw, model, dtex, ntex):
         o.close()
+
+
+def test_pipelined_submissions_equal_serial_ones(hana):
+    """Back-to-back submissions are pipelined (the next submission is binned on side streams, with the scratch
+    sets and uniform block of the other parity, while the current one is rasterised). Six batches with different cameras
+    and two scenes, queued without a synchronising call in between into one ring and into two alternating rings, must give
+    the frames a context with HANA_NO_PIPELINE=1 gives, bit for bit."""
+    import os
+    W, Hh, F = 480, 270, 5
+    blob = hana.synthetic_scene("blob")
+    a2v = hana.scene.synthetic_grid(60, 40, seed=9)
+    dif, nm = hana.scene.noise_textures(9, 64, flat_normal=True)
+    grid = hana.Scene("grid", a2v, dif, nm)
+    batches = [hana.orbit_sweep_uniforms(W, Hh, 11 * k, F, frames_per_turn=64) for k in range(6)]
+
+    def run(pipelined):
+        old = os.environ.pop("HANA_NO_PIPELINE", None)
+        if not pipelined:
+            os.environ["HANA_NO_PIPELINE"] = "1"
+        try:
+            ctx = hana.Context(0)
+        finally:
+            os.environ.pop("HANA_NO_PIPELINE", None)
+            if old is not None:
+                os.environ["HANA_NO_PIPELINE"] = old
+        objs = [blob.upload(ctx), grid.upload(ctx)]
+        rings = [ctx.sweep(W, Hh, F), ctx.sweep(W, Hh, F)]
+        # six submissions queued back to back (nothing synchronises the host in between), alternating rings, scenes and
+        # shaders: what the last two left in the rings
+        for k, b in enumerate(batches):
+            o = objs[k & 1]
+            rings[k & 1].render(o[0], hana.BLINN if k % 3 else hana.NORMALMAP, b, o[1], o[2])
+        sums = [rings[0].checksums(F), rings[1].checksums(F)]
+        # two rings alternating, frames read after the NEXT submission has been queued
+        frames = []
+        for k, b in enumerate(batches):
+            o = objs[(k >> 1) & 1]
+            rings[k & 1].render(o[0], hana.BLINN, b, o[1], o[2])
+            if k:
+                frames.append(np.stack([rings[(k - 1) & 1].download(i)[0] for i in range(F)]))
+        frames.append(np.stack([rings[(len(batches) - 1) & 1].download(i)[0] for i in range(F)]))
+        assert rings[0].overflow_count() == 0 and rings[1].overflow_count() == 0
+        for r in rings:
+            r.close()
+        for o in objs:
+            for x in o:
+                x.close()
+        ctx.close()
+        return sums, frames
+
+    s_pipe, f_pipe = run(True)
+    s_ser, f_ser = run(False)
+    for k in range(2):
+        assert np.array_equal(s_pipe[k], s_ser[k]), "ring %d after six queued submissions" % k
+    for k in range(len(batches)):
+        assert np.array_equal(f_pipe[k], f_ser[k]), "batch %d (two rings)" % k
