@@ -220,7 +220,13 @@ HANA_API int hana_last_stats(hana_ctx* ctx, HanaStats* out); /* synchronises */
  * checksums, stats, device_ptrs, hana_sync, hana_timer_stop) waits for it and,
  * if the batch ran out of internal scratch, transparently renders it again
  * with more. Model, textures and a device uniform buffer must stay alive and
- * unchanged until then. */
+ * unchanged until then.
+ * Consecutive submissions of a context are PIPELINED: the uniform upload and the binning of both passes of a
+ * submission run on internal streams beside the rasterisers of the submission before it (their scratch and uniform
+ * blocks alternate), the rasterisers follow in submission order on the context's stream. Nothing changes for the
+ * caller except that inputs handed to a render (model, textures, uniform buffers) must be COMPLETE when the call is
+ * made, not merely queued on some stream. A context that runs on a caller's stream (hana_ctx_set_stream), or
+ * HANA_NO_PIPELINE=1 in the environment, keeps everything in that one stream's order. */
 HANA_API int hana_sweep_create(hana_ctx* ctx, int width, int height, int max_frames, hana_sweep** out);
 HANA_API int hana_sweep_destroy(hana_sweep* s);
 /* uniforms: host array of n_frames HanaUniforms (copied H2D inside). */
