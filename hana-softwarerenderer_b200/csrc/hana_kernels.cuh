@@ -38,7 +38,10 @@ constexpr int TILE_PIX = TILE * TILE;
 constexpr int TILE_BITS = 20;        /* work item = frame << 20 | tile_y << 10 | tile_x */
 constexpr uint32_t TILE_MASK = (1u << TILE_BITS) - 1u;
 constexpr uint32_t WORK_INVALID = 0xFFFFFFFFu;
-constexpr int SETUP_THREADS = 256;
+#ifndef HANA_SETUP_THREADS
+#define HANA_SETUP_THREADS 256
+#endif
+constexpr int SETUP_THREADS = HANA_SETUP_THREADS;
 #ifndef HANA_SETUP_CTAS
 #define HANA_SETUP_CTAS 3 /* resident CTAs per SM setup_kernel is compiled for */
 #endif
@@ -215,7 +218,7 @@ constexpr int MAX_ATTR_QUADS = 7;
  *   q2 = bbx, bby, triangle index (attribute block), order key      q3 = d0, d1, d2, 1/uz   (covered pixels only) */
 template <int SHADER>
 __device__ __forceinline__ void store_triangle(const PassParams& p, int f, uint32_t slot, const TriRecord& r,
-                                               const float* v0, const float* v1, const float* v2) {
+                                               const float* v0, const float* v1, const float* v2, bool with_range = true) {
     constexpr int NA = ShaderAttrs<SHADER>::NA;
     constexpr int NQ = ShaderAttrs<SHADER>::NQ;
     float4* dst = p.tri_rec + ((size_t)f * p.tri_cap + slot) * 4;
@@ -223,7 +226,7 @@ __device__ __forceinline__ void store_triangle(const PassParams& p, int f, uint3
     dst[1] = make_float4(r.s1x, r.s1y, r.uz, r.thr);
     dst[2] = make_float4(__uint_as_float(r.bbx), __uint_as_float(r.bby), __uint_as_float(slot), __uint_as_float(r.key));
     dst[3] = make_float4(r.d0, r.d1, r.d2, r.ruz);
-    p.tri_bbox[(size_t)f * p.tri_cap + slot] = make_uint2(r.bbx, r.bby);
+    if (with_range) p.tri_bbox[(size_t)f * p.tri_cap + slot] = make_uint2(r.bbx, r.bby); /* a micro-triangle's slot gets the empty range instead */
     float a[(NQ - 1) * 4];
 #pragma unroll
     for (int k = 0; k < NA; k++) {
@@ -334,7 +337,8 @@ __global__ void __launch_bounds__(SETUP_THREADS, HANA_SETUP_CTAS) setup_kernel(c
     bool listed = false; /* the pair kernels have to look at this slot */
     if (face < p.nfaces && (uint32_t)face < p.tri_cap) {
         if (emit) {
-            store_triangle<SHADER>(p, f, (uint32_t)face, r, v, v + V2F_N, v + 2 * V2F_N);
+            const bool micro = p.vis && (int)(r.bbx >> 16) - (int)(r.bbx & 0xFFFFu) < MICRO_EXTENT && (int)(r.bby >> 16) - (int)(r.bby & 0xFFFFu) < MICRO_EXTENT && r.uz < 0.f;
+            store_triangle<SHADER>(p, f, (uint32_t)face, r, v, v + V2F_N, v + 2 * V2F_N, !micro);
             /* Micro-triangles (pixel range at most MICRO_EXTENT on a side: a dense mesh has millions, BASELINE.json configs[3]) do not go
              * through the tile lists, where the tile's warp would walk them one by one. Their pixels are tested right
              * here with the scalar statement of the coverage / weight / depth arithmetic (hana_core.cuh: the bits the tile
@@ -342,7 +346,7 @@ __global__ void __launch_bounds__(SETUP_THREADS, HANA_SETUP_CTAS) setup_kernel(c
              * visibility buffer: smallest depth first, then the largest order key (graphics.cpp:359 in submission order).
              * The tile rasteriser starts from that buffer and recomputes the winner's weights when it shades. */
             const int x0 = (int)(r.bbx & 0xFFFFu), x1 = (int)(r.bbx >> 16), y0 = (int)(r.bby & 0xFFFFu), y1 = (int)(r.bby >> 16);
-            if (p.vis && x1 - x0 < MICRO_EXTENT && y1 - y0 < MICRO_EXTENT && r.uz < 0.f) {
+            if (micro) {
                 uint32_t touched = 0; /* tiles (at most 2 x 2: MICRO_EXTENT <= 16) that got a fragment: bit (ty - ty0) * 2 + (tx - tx0) */
                 const int tx_o = x0 >> 4, ty_o = y0 >> 4;
                 for (int y = y0; y <= y1; y++) {
@@ -379,7 +383,7 @@ __global__ void __launch_bounds__(SETUP_THREADS, HANA_SETUP_CTAS) setup_kernel(c
     }
     const unsigned live = __ballot_sync(0xFFFFFFFFu, emit);
     if (lane == 0 && live) atomicAdd(p.tri_count + (size_t)f * TRI_COUNT_WAYS + (blockIdx.x & (TRI_COUNT_WAYS - 1)), (uint32_t)__popc(live));
-    count_aggregated(p.tile_count + (size_t)f * p.tile_pad, key);
+    if (__ballot_sync(0xFFFFFFFFu, key >= 0)) count_aggregated(p.tile_count + (size_t)f * p.tile_pad, key); /* warp-uniform */
 }
 
 /* ---- scan: per frame, tile counts -> offsets into the pool + work queue ---- */
