@@ -123,3 +123,31 @@ def test_device_files_of_crafted_frames(hana, ctx, tmp_path):
             want = host_file(hana, tmp_path, frames[f], "c%d.tga" % f)
             assert files[f] == want, "crafted frame %d (%dx%d, kind %d): device file differs" % (f, W, Hh, f % 5)
         sw.close()
+
+
+@pytest.mark.gpu
+def test_device_files_of_large_frames(hana, ctx, tmp_path):
+    """BASELINE.json configs[3] / configs[4] frame sizes (3840x2160, 7680x4320): 260 k / 1 M words per frame, spans of 254 /
+    1013 words per thread of the structure kernel, batch offsets beyond 2^24 — crafted streams, byte for byte."""
+    import torch
+    from hana_softwarerenderer_b200.sharding import device_plane_tensor
+    rng = np.random.RandomState(8)
+    for (W, Hh, kinds) in ((3840, 2160, (1, 0)), (7680, 4320, (1,))):
+        F = len(kinds)
+        sw = ctx.sweep(W, Hh, F)
+        cptr, _, stride = sw.device_planes()
+        ring = device_plane_tensor(cptr, stride * 4 * F, "cuda:0")
+        frames = []
+        for kind in kinds:
+            px = crafted_stream(rng, W * Hh, kind)
+            rgba = np.zeros((Hh, W, 4), np.uint8)
+            rgba[::-1, :, :3] = np.stack([(px >> 16) & 255, (px >> 8) & 255, px & 255], -1).astype(np.uint8).reshape(Hh, W, 3)
+            rgba[..., 3] = 7
+            frames.append(rgba)
+        ring.copy_(torch.from_numpy(np.stack(frames).reshape(-1)))
+        torch.cuda.synchronize()
+        files = sw.tga_files(0, F)
+        for f in range(F):
+            want = host_file(hana, tmp_path, frames[f], "L%d.tga" % f)
+            assert len(files[f]) == len(want) and files[f] == want, "large crafted frame %dx%d kind %d: device file differs" % (W, Hh, kinds[f])
+        sw.close()
