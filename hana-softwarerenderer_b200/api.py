@@ -98,6 +98,7 @@ def load():
         "hana_ctx_launch_count": [vp, C.POINTER(C.c_uint64)],
         "hana_ctx_uses_tma": [vp],
         "hana_ctx_set_tma": [vp, i],
+        "hana_ctx_set_pipeline": [vp, i],
         "hana_ctx_sm_count": [vp],
         "hana_ctx_wide_r8_launches": [vp, C.POINTER(C.c_uint64)],
         "hana_timer_start": [vp],
@@ -211,6 +212,10 @@ class Context:
 
     def set_tma(self, enable):
         _ck(self.L.hana_ctx_set_tma(self.h, int(enable)))
+
+    def set_pipeline(self, enable):
+        """Pipelined sweep submissions on / off (on by default); waits for the work queued so far."""
+        _ck(self.L.hana_ctx_set_pipeline(self.h, int(bool(enable))))
 
     @property
     def sm_count(self):

@@ -403,6 +403,12 @@ extern "C" int hana_ctx_set_tma(hana_ctx* ctx, int enable) {
     return HANA_OK;
 }
 extern "C" int hana_ctx_sm_count(hana_ctx* ctx) { return ctx ? ctx->sm_count : 0; }
+extern "C" int hana_ctx_set_pipeline(hana_ctx* ctx, int enable) {
+    if (!ctx) return fail(HANA_E_INVALID, "ctx is NULL");
+    HANA_TRY(hana_sync(ctx));
+    ctx->pipeline = enable != 0;
+    return HANA_OK;
+}
 extern "C" int hana_ctx_wide_r8_launches(hana_ctx* ctx, uint64_t* out) {
     if (!ctx || !out) return fail(HANA_E_INVALID, "NULL argument");
     *out = ctx->wide_r8_launches;

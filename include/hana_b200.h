@@ -114,6 +114,10 @@ HANA_API int hana_ctx_launch_count(hana_ctx* ctx, uint64_t* out);
  * plain global stores. HANA_NO_TMA=1 in the environment selects the latter at creation. */
 HANA_API int hana_ctx_uses_tma(hana_ctx* ctx);
 HANA_API int hana_ctx_set_tma(hana_ctx* ctx, int enable);
+/* Pipelined sweep submissions (see hana_sweep_create) on / off; waits for the work queued so far. On by default unless
+ * HANA_NO_PIPELINE=1 is in the environment at creation. Off = one submission after the other in the context's stream,
+ * which is also what gives per-kernel profile times that add up to the step. */
+HANA_API int hana_ctx_set_pipeline(hana_ctx* ctx, int enable);
 HANA_API int hana_ctx_sm_count(hana_ctx* ctx);
 /* Shadow-map passes that took the wide-slot rasteriser (a pass whose per-frame triangle capacity exceeds what the
  * 24-bit slot field of the packed {shadow byte, triangle slot} state addresses; HANA_R8_SLOT_LIMIT in the environment
